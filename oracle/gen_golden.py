@@ -1,0 +1,270 @@
+"""TEST INFRASTRUCTURE ONLY — generates tests/golden/*.npz by running the
+UNMODIFIED reference (/root/reference) in the build container.
+
+    python oracle/gen_golden.py            # regenerates every fixture
+
+One subprocess per (board size, config) because the reference freezes
+conf['SIZE'] / MCTS_BATCH_SIZE / ENERGY at import time (play.py:14,
+self_play.py:22-23, nomodel_self_play.py:21).  The fixtures are what pins the C
+oracle (oracle/go_oracle.c) and, through it, the CUDA engine.  Randomness the
+reference draws from MT19937 (np.random.choice, np.random.dirichlet,
+random.random, random.choice) is RECORDED here and INJECTED in the parity tests.
+"""
+import os
+import sys
+import json
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _setup(size, overrides=None):
+    sys.path.insert(0, ROOT)
+    from oracle import ref_harness as rh
+    ns = rh.load(size, overrides=overrides or {})
+    return ns
+
+
+def tree_rows(node, depth=0, rows=None):
+    """Canonical pre-order serialisation of a reference dict tree:
+    rows of (depth, move, count, value f32, mean f32, p f64, busy, expanded)."""
+    import numpy as np
+    if rows is None:
+        rows = []
+    for m, c in node['subtree'].items():
+        rows.append((depth, m, c['count'], float(np.float32(c['value'])), float(np.float32(c['mean_value'])),
+                     float(c['p']), c.get('virtual_loss', 0), 1 if c['subtree'] else 0))
+        tree_rows(c, depth + 1, rows)
+    return rows
+
+
+def pack_rows(rows):
+    import numpy as np
+    a = np.zeros(len(rows), dtype=[('depth', 'i4'), ('move', 'i4'), ('count', 'i8'), ('value', 'f4'),
+                                   ('mean', 'f4'), ('p', 'f8'), ('busy', 'i4'), ('expanded', 'i4')])
+    for i, r in enumerate(rows):
+        a[i] = r
+    return a
+
+
+# ------------------------------------------------------------------- rules
+def gen_rules(size, ngames, seed):
+    import numpy as np, random
+    ns = _setup(size)
+    from oracle import oracle as o          # only for the packing helper
+    play = ns.play
+    rng = random.Random(seed)
+    S, A = size, size * size + 1
+    all_moves, all_states, all_masks, results = [], [], [], []
+    for g in range(ngames):
+        board, _ = play.game_init()
+        moves, states, masks = [], [], []
+        passes = 0
+        for t in range(2 * S * S):
+            m = play.legal_moves(board)
+            states.append(o.pack_board(np.ascontiguousarray(board, dtype=np.int32)))
+            masks.append(m.astype(np.uint8))
+            empties = [i for i in range(S * S) if board[0, i // S, i % S, 0] == 0 and board[0, i // S, i % S, 1] == 0]
+            legal = [i for i in range(S * S) if m[i] == 0]
+            r = rng.random()
+            if r < 0.02 or not legal:
+                mv = S * S
+            elif r < 0.08 and empties:
+                mv = rng.choice(empties)      # includes suicides / ko retakes: make_play executes them (Q5)
+            else:
+                mv = rng.choice(legal)
+            x, y = (0, S) if mv == S * S else (mv % S, mv // S)
+            play.make_play(x, y, board)
+            moves.append(mv)
+            passes = passes + 1 if mv == S * S else 0
+            if passes == 2:
+                break
+        states.append(o.pack_board(np.ascontiguousarray(board, dtype=np.int32)))
+        masks.append(play.legal_moves(board).astype(np.uint8))
+        w, b, wh = play.get_winner(board)
+        all_moves.append(np.array(moves, np.int32))
+        all_states.append(np.array(states, np.uint32))
+        all_masks.append(np.array(masks, np.uint8))
+        results.append((w, float(b), float(wh)))
+    offs = np.cumsum([0] + [len(m) for m in all_moves]).astype(np.int64)
+    np.savez_compressed(os.path.join(OUT, "rules_s%d.npz" % size), size=size, komi=5.5,
+                        move_offsets=offs, moves=np.concatenate(all_moves),
+                        states=np.concatenate(all_states), masks=np.concatenate(all_masks),
+                        results=np.array(results, np.float64))
+
+
+# ---------------------------------------------------------------- symmetry
+def gen_symmetry(size):
+    import numpy as np
+    ns = _setup(size)
+    sym = ns.symmetry
+    S, A = size, size * size + 1
+    fwd = [sym._id, sym.left_diagonal, sym.vertical_axis, sym.horizontal_axis,
+           sym.rotation_90, sym.rotation_180, sym.rotation_270, sym.right_diagonal]
+    rev = [sym._id, sym.reverse_left_diagonal, sym.reverse_vertical_axis, sym.reverse_horizontal_axis,
+           sym.reverse_rotation_90, sym.reverse_rotation_180, sym.reverse_rotation_270, sym.reverse_right_diagonal]
+    btab = np.zeros((8, S * S), np.int32)
+    ptab = np.zeros((8, A), np.int32)
+    for k in range(8):
+        idx = np.arange(S * S, dtype=np.int32).reshape(1, S, S, 1).repeat(17, axis=3)
+        btab[k] = np.array(fwd[k](np.copy(idx)))[0, :, :, 0].reshape(-1)      # out[i] = in[btab[i]]
+        pol = np.arange(A, dtype=np.float32).reshape(1, A)
+        ptab[k] = np.array(rev[k](np.copy(pol)))[0].astype(np.int32)
+    order = [f.__name__ for f, _ in sym.SYMMETRIES]
+    np.savez_compressed(os.path.join(OUT, "symmetry_s%d.npz" % size), size=size, board_src=btab, policy_src=ptab,
+                        symmetries=np.array(order))
+
+
+# -------------------------------------------------------------------- mcts
+def gen_mcts(size, mode, batch, steps, plies, seed, tag):
+    """Search trace: a noised root, `steps` simulate/wave calls per ply, the full
+    tree after every ply, then a prescribed pick + re-root (self_play.py:223-238)."""
+    import numpy as np
+    ns = _setup(size, overrides={'ENERGY': batch, 'MCTS_BATCH_SIZE': batch})
+    from oracle.fake_eval import evaluate, FakeModel
+    ns.symmetry.SYMMETRIES = ns.symmetry.SYMMETRIES[0:1]
+    play = ns.play
+    S, A = size, size * size + 1
+    model = FakeModel(sharp=True, salt=seed)
+    ns.evaluator = lambda ind, board: (lambda p, v: (p[0], v[0]))(*evaluate(board, seed, True))
+    np.random.seed(seed)
+    noise = np.random.dirichlet([0.03] * A)
+    play.np.random.dirichlet = lambda a: noise
+    board, _ = play.game_init()
+    pol, _ = model.predict_on_batch(board)
+    tree = play.new_tree(pol[0], board, add_noise=True)
+    trees, picks, t0picks, newtree = [], [], [], []
+    for ply in range(plies):
+        op = board[0, 0, 0, -1]
+        for i in range(steps):
+            if mode == 'a':
+                ns.self_play.simulate(tree, np.copy(board), model, batch, op)
+            else:
+                ns.nomodel_self_play.async_simulate2(tree, np.copy(board), "BEST", batch, op, 0)
+        trees.append(pack_rows(tree_rows(tree)))
+        _, _, t0 = max((d['count'], d['mean_value'], a) for a, d in tree['subtree'].items())
+        t0picks.append(t0)
+        sel = t0
+        if ply % 3 == 1:                      # a recorded "temperature 1" style pick
+            vis = [a for a, d in tree['subtree'].items() if d['count'] > 0]
+            sel = vis[(ply * 7) % len(vis)]
+        picks.append(sel)
+        tree = tree['subtree'][sel]
+        tree['parent'] = None
+        x, y = (0, S) if sel == S * S else (sel % S, sel // S)
+        play.make_play(x, y, board)
+        nt = 0
+        if not tree['subtree']:
+            pol, _ = model.predict_on_batch(board)
+            tree = play.new_tree(pol[0], board)
+            nt = 1
+        newtree.append(nt)
+    offs = np.cumsum([0] + [len(t) for t in trees]).astype(np.int64)
+    np.savez_compressed(os.path.join(OUT, "mcts_%s.npz" % tag), size=size, mode=mode, batch=batch, steps=steps,
+                        seed=seed, noise=noise, tree_offsets=offs, trees=np.concatenate(trees),
+                        picks=np.array(picks, np.int32), t0picks=np.array(t0picks, np.int32),
+                        newtree=np.array(newtree, np.int32))
+
+
+# --------------------------------------------------------------- game loop
+def gen_game(size, mode, batch, sims, stop_exploration, self_play, num_moves, seed, tag, resign=None):
+    """Full play_game / play_game_async run with recorded RNG draws."""
+    import numpy as np, random
+    ns = _setup(size, overrides={'ENERGY': batch, 'MCTS_BATCH_SIZE': batch, 'MCTS_SIMULATIONS': sims})
+    from oracle.fake_eval import evaluate, FakeModel
+    from oracle import oracle as o
+    ns.symmetry.SYMMETRIES = ns.symmetry.SYMMETRIES[0:1]
+    play = ns.play
+    S, A = size, size * size + 1
+    random.seed(seed)
+    np.random.seed(seed)
+    rec = dict(choice=[], noise=[], coin=[])
+    real_choice = np.random.choice
+    real_dir = np.random.dirichlet
+
+    def choice(moves, size=1, p=None):
+        r = real_choice(moves, size=size, p=p)
+        rec['choice'].append(int(r[0]))
+        return r
+
+    def dirichlet(alpha):
+        r = real_dir(alpha)
+        rec['noise'].append(np.array(r))
+        return r
+
+    import play as _play_mod
+    real_random = _play_mod.random
+
+    def coin():
+        r = real_random()
+        rec['coin'].append(r)
+        return r
+
+    _play_mod.random = coin
+    _play_mod.np.random.dirichlet = dirichlet
+    m1 = FakeModel("model_1", salt=seed, sharp=True)
+    m2 = FakeModel("model_2", salt=seed + 1, sharp=True)
+    if mode == 'a':
+        ns.self_play.np.random.choice = choice
+        if self_play:
+            m2 = m1
+        gd = ns.self_play.play_game(m1, m2, sims, stop_exploration, self_play=self_play, num_moves=num_moves,
+                                    resign_model1=resign, resign_model2=resign)
+        calls = np.array(m1.calls + [-1] + (m2.calls if m2 is not m1 else []), np.int64)
+    else:
+        ns.nomodel_self_play.np.random.choice = choice
+        salts = {"BEST_SYM": seed, "LATEST_SYM": seed + 1, "BEST": seed, "LATEST": seed + 1}
+        ns.names = {"BEST_SYM": "model_1", "LATEST_SYM": "model_2", "BEST": "model_1", "LATEST": "model_2"}
+        ns.evaluator = lambda ind, board: (lambda p, v: (p[0], v[0]))(*evaluate(board, salts[ind], True))
+        i1, i2 = ("BEST_SYM", "BEST_SYM") if self_play else ("BEST_SYM", "LATEST_SYM")
+        gd = ns.nomodel_self_play.play_game_async(i1, i2, batch, stop_exploration, 0, self_play=self_play,
+                                                  num_moves=num_moves, resign_model1=resign, resign_model2=resign)
+        calls = np.zeros(0, np.int64)
+    mv = gd['moves']
+    np.savez_compressed(
+        os.path.join(OUT, "game_%s.npz" % tag), size=size, mode=mode, batch=batch, sims=sims,
+        stop_exploration=stop_exploration, self_play=int(self_play), num_moves=-1 if num_moves is None else num_moves,
+        seed=seed, resign=np.nan if resign is None else resign,
+        choice=np.array(rec['choice'], np.int32), noise=np.array(rec['noise'], np.float64).reshape(-1, A),
+        coin=np.array(rec['coin'], np.float64),
+        boards=np.array([o.pack_board(np.ascontiguousarray(m['board'], dtype=np.int32)) for m in mv], np.uint32),
+        policy=np.array([m['policy'] for m in mv], np.float64),
+        value=np.array([np.float32(m['value']) for m in mv], np.float32).reshape(-1),
+        move=np.array([m['move'] for m in mv], np.int32), move_n=np.array([m['move_n'] for m in mv], np.int32),
+        player=np.array([m['player'] for m in mv], np.int32),
+        modelB_name=gd['modelB_name'], modelW_name=gd['modelW_name'],
+        winner=-1 if gd['winner'] is None else gd['winner'], winner_model=str(gd['winner_model']),
+        result=gd['result'], calls=calls)
+
+
+JOBS = [
+    ("rules", dict(size=9, ngames=12, seed=1)),
+    ("rules", dict(size=19, ngames=3, seed=2)),
+    ("rules", dict(size=5, ngames=20, seed=3)),
+    ("symmetry", dict(size=9)),
+    ("symmetry", dict(size=19)),
+    ("mcts", dict(size=9, mode='a', batch=8, steps=8, plies=10, seed=3, tag="a_s9")),
+    ("mcts", dict(size=9, mode='b', batch=8, steps=8, plies=10, seed=4, tag="b_s9")),
+    ("mcts", dict(size=5, mode='a', batch=100, steps=2, plies=30, seed=5, tag="a_s5_wide")),
+    ("mcts", dict(size=3, mode='b', batch=8, steps=4, plies=18, seed=6, tag="b_s3_stall")),
+    ("mcts", dict(size=19, mode='a', batch=100, steps=2, plies=2, seed=7, tag="a_s19")),
+    ("mcts", dict(size=19, mode='b', batch=8, steps=12, plies=2, seed=8, tag="b_s19")),
+    ("game", dict(size=9, mode='a', batch=8, sims=32, stop_exploration=6, self_play=True, num_moves=14, seed=11, tag="a_selfplay_s9")),
+    ("game", dict(size=9, mode='a', batch=8, sims=32, stop_exploration=0, self_play=False, num_moves=10, seed=12, tag="a_eval_s9")),
+    ("game", dict(size=5, mode='a', batch=8, sims=16, stop_exploration=4, self_play=True, num_moves=None, seed=13, tag="a_selfplay_s5_full")),
+    ("game", dict(size=9, mode='b', batch=8, sims=32, stop_exploration=6, self_play=True, num_moves=14, seed=14, tag="b_selfplay_s9")),
+    ("game", dict(size=9, mode='b', batch=8, sims=32, stop_exploration=0, self_play=False, num_moves=10, seed=15, tag="b_eval_s9")),
+    ("game", dict(size=9, mode='a', batch=8, sims=16, stop_exploration=3, self_play=True, num_moves=None, seed=16, tag="a_resign_s9", resign=0.5)),
+]
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        kind, kw = sys.argv[1], json.loads(sys.argv[2])
+        {"rules": gen_rules, "symmetry": gen_symmetry, "mcts": gen_mcts, "game": gen_game}[kind](**kw)
+    else:
+        os.makedirs(OUT, exist_ok=True)
+        for kind, kw in JOBS:
+            print(kind, kw, flush=True)
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), kind, json.dumps(kw)], cwd="/tmp")

@@ -1,0 +1,33 @@
+import os
+import sys
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "ref: needs the reference checkout at /root/reference (build container only)")
+
+
+def pytest_collection_modifyitems(config, items):
+    have_ref = os.path.isfile(os.path.join(os.environ.get("SEJONGGO_REFERENCE", "/root/reference"), "play.py"))
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        have_gpu = False
+    for item in items:
+        if "ref" in item.keywords and not have_ref:
+            item.add_marker(pytest.mark.skip(reason="reference checkout not present"))
+        if "gpu" in item.keywords and not have_gpu:
+            item.add_marker(pytest.mark.skip(reason="no CUDA device"))
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
