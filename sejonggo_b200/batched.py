@@ -1,0 +1,351 @@
+"""BatchedGames — G concurrent games advanced in lock-step on one GPU.
+
+This is the batched form of the reference's two game drivers:
+  mode 'a'  self_play.play_game          (self_play.py:164-290; search self_play.py:28-152)
+  mode 'b'  nomodel_self_play.play_game_async (nomodel_self_play.py:142-271; waves :59-82)
+Every per-game decision (tree reuse, noise only on new trees, temperature switch,
+pass/pass and 2*S*S termination, resignation, value sign, quirks Q12-Q17) follows
+the reference; what changes is that the rules, the tree and (with a TowerModel)
+the network all stay in HBM and one kernel launch serves all games.
+
+Randomness: `rng` must provide coin()/dirichlet(n)/symmetry()/choice(moves, ps);
+the default HostRng draws from numpy like the reference.  Parity tests inject
+recorded draws.
+"""
+import numpy as np
+import torch
+
+from .engine import Engine, EngineError
+
+
+class HostRng(object):
+    def __init__(self, seed=None, alpha=0.03):
+        self.r = np.random.RandomState(seed)
+        self.alpha = alpha
+        self.device_pick = True      # temperature-1 picks sampled on the device from u01
+
+    def coin(self):
+        return float(self.r.random_sample())
+
+    def dirichlet(self, n):
+        return self.r.dirichlet([self.alpha] * n)
+
+    def symmetry(self):
+        return int(self.r.randint(7))          # random.choice over the 7 SYMMETRIES (symmetry.py:117-128)
+
+    def uniform(self):
+        return float(self.r.random_sample())
+
+    def choice(self, moves, ps):
+        return int(self.r.choice(moves, size=1, p=ps)[0])
+
+
+class HostModelAdapter(object):
+    """Evaluator over the reference's duck-typed model protocol
+    (`.predict_on_batch(X[n,S,S,17]) -> (policy[n,A], value[n,1])`, `.name`)."""
+
+    def __init__(self, model):
+        self.model = model
+        self.name = getattr(model, "name", "model")
+
+    def evaluate(self, engine, which, idx, syms):
+        """idx: int64 device tensor of position indices (games or leaf slots);
+        syms: int32 device tensor [len(idx)] or None.  Returns device (policy [k,A], value [k])."""
+        k = int(idx.numel())
+        lim = engine.G * engine.L if which else engine.G
+        if syms is None:
+            planes = engine.export_planes(which, 0, lim)[idx]
+        else:
+            full = torch.zeros(lim, dtype=torch.int32, device=engine.device)
+            full[idx] = syms
+            planes = engine.export_planes(which, 0, lim, syms=full)[idx]
+        p, v = self.model.predict_on_batch(planes.cpu().numpy())
+        p = torch.as_tensor(np.ascontiguousarray(p, dtype=np.float32)).to(engine.device).reshape(k, engine.A)
+        v = torch.as_tensor(np.ascontiguousarray(v, dtype=np.float32)).to(engine.device).reshape(k)
+        if syms is not None:
+            p = engine.policy_unsym(p, syms=syms)
+        return p, v
+
+
+def as_evaluator(model):
+    if hasattr(model, "evaluate") and hasattr(model, "is_sgo_evaluator"):
+        return model
+    return HostModelAdapter(model)
+
+
+class BatchedGames(object):
+    def __init__(self, models, n_games, size=19, mode='a', mcts_batch_size=100, energy=8, mcts_simulations=1600,
+                 stop_exploration=30, self_play=False, num_moves=None, resign=(None, None), komi=5.5,
+                 dirichlet_eps=0.25, use_symmetry=True, root_symmetry=None, rng=None, rngs=None, arena_blocks=None,
+                 device=0, record_boards='full', engine=None):
+        """models: (model1, model2); pass the same object twice for self-play.
+        resign: (resign_model1, resign_model2), each None, a float, or an array[G].
+        rngs: optional list of per-game rng objects (parity runs); else one shared `rng`."""
+        self.m1, self.m2 = models
+        self.same_model = self.m1 is self.m2
+        self.ev = [as_evaluator(self.m1), as_evaluator(self.m1) if self.same_model else as_evaluator(self.m2)]
+        if self.same_model:
+            self.ev[1] = self.ev[0]
+        self.G, self.S, self.A = n_games, size, size * size + 1
+        self.mode = mode
+        self.batch = mcts_batch_size if mode == 'a' else energy
+        self.energy = energy
+        self.sims = mcts_simulations
+        self.stop_exploration = stop_exploration
+        self.self_play = self_play
+        self.num_moves = size * size * 2 if num_moves is None else num_moves
+        self.komi = komi
+        self.eps = dirichlet_eps
+        self.use_symmetry = use_symmetry
+        # mode A evaluates the root without symmetry (self_play.py:187); mode B's *_SYM tags
+        # send the root through random_symmetry_predict too (predicting_queue_worker.py:88-92)
+        self.root_symmetry = (mode == 'b') if root_symmetry is None else root_symmetry
+        self.rngs = rngs if rngs is not None else [rng or HostRng()] * n_games
+        self.record_boards = record_boards
+        steps = int(self.sims / self.batch)
+        if arena_blocks is None:
+            arena_blocks = max(64, 4 * (steps * self.batch + 2))
+        T = 1 if self_play else 2
+        self.eng = engine or Engine(size=size, n_games=n_games, trees_per_game=T, max_leaves=self.batch,
+                                    arena_blocks=arena_blocks, komi=komi, device=device)
+        self.resign = [self._per_game(resign[0]), self._per_game(resign[1])]
+        self.sim_count = 0            # leaves expanded + backed up (the north-star "simulations")
+        self.eval_count = 0
+        self.plies_done = 0
+
+    def _per_game(self, r):
+        if r is None:
+            return np.full(self.G, np.nan)
+        return np.broadcast_to(np.asarray(r, dtype=np.float64), (self.G,)).copy()
+
+    # --------------------------------------------------------------- pieces
+    def _evaluate(self, which, idx_list, model_of_game, syms_of_game):
+        """Evaluate positions `idx_list` (numpy int64: games or leaf slots).  Returns dense device
+        buffers policy [lim, A], value [lim] with rows of idx filled."""
+        e = self.eng
+        lim = e.G * e.L if which else e.G
+        policy = torch.zeros((lim, e.A), dtype=torch.float32, device=e.device)
+        value = torch.zeros((lim,), dtype=torch.float32, device=e.device)
+        if len(idx_list) == 0:
+            return policy, value
+        games = idx_list // e.L if which else idx_list
+        for mi in ((0,) if self.same_model else (0, 1)):
+            sel = idx_list if self.same_model else idx_list[model_of_game[games] == mi]
+            if len(sel) == 0:
+                continue
+            idx = torch.as_tensor(sel, dtype=torch.int64, device=e.device)
+            syms = None
+            if syms_of_game is not None:
+                g = sel // e.L if which else sel
+                syms = torch.as_tensor(syms_of_game[g], dtype=torch.int32, device=e.device)
+            p, v = self.ev[mi].evaluate(e, which, idx, syms)
+            policy[idx] = p
+            value[idx] = v
+            self.eval_count += len(sel)
+        return policy, value
+
+    def _search_a(self, tree_sel, active, model_of_game):
+        e = self.eng
+        for _ in range(int(self.sims / self.batch)):                    # self_play.py:128
+            e.select_a(self.batch, tree_sel)
+            counts = e.leaf_counts().cpu().numpy()
+            slots = np.concatenate([g * e.L + np.arange(counts[g]) for g in range(self.G)]).astype(np.int64) \
+                if counts.sum() else np.zeros(0, np.int64)
+            syms = None
+            if self.use_symmetry:                                       # one draw per game per batch (symmetry.py:128)
+                syms = np.zeros(self.G, np.int32)
+                for g in np.nonzero(active)[0]:
+                    syms[g] = self.rngs[g].symmetry()
+            policy, value = self._evaluate(1, slots, model_of_game, syms)
+            e.expand(policy, value, tree_sel)
+            e.backup_a(tree_sel)
+            self.sim_count += int(counts.sum())
+
+    def _search_b(self, tree_sel, active, model_of_game):
+        e = self.eng
+        for _ in range(int(self.sims / self.energy)):                   # nomodel_self_play.py:116
+            restart = True
+            prev = np.zeros(self.G, np.int64)
+            while True:
+                newly, stalled = e.select_b(self.batch, restart, tree_sel)
+                restart = False
+                if newly == 0:
+                    break
+                counts = e.leaf_counts().cpu().numpy().astype(np.int64)
+                slots = np.concatenate([g * e.L + np.arange(prev[g], counts[g]) for g in range(self.G)]).astype(np.int64)
+                prev = counts
+                policy = torch.zeros((e.G * e.L, e.A), dtype=torch.float32, device=e.device)
+                value = torch.zeros((e.G * e.L,), dtype=torch.float32, device=e.device)
+                # put_predict_request: one request (and one symmetry draw) per leaf, in issue order
+                for s in slots:
+                    g = int(s // e.L)
+                    sy = None
+                    if self.use_symmetry:
+                        sy = np.zeros(self.G, np.int32)
+                        sy[g] = self.rngs[g].symmetry()
+                    p1, v1 = self._evaluate(1, np.array([s], np.int64), model_of_game, sy)
+                    policy[s] = p1[s]
+                    value[s] = v1[s]
+                e.expand(policy, value, tree_sel)
+                self.sim_count += len(slots)
+                if stalled == 0:
+                    break
+            e.backup_b(self.energy, tree_sel)
+
+    def _search_b_fast(self, tree_sel, active, model_of_game):
+        """Mode B with one batched evaluation per wave phase (throughput path).  Identical
+        tree results to _search_b; only the order of host RNG symmetry draws across games differs."""
+        e = self.eng
+        for _ in range(int(self.sims / self.energy)):
+            restart = True
+            prev = np.zeros(self.G, np.int64)
+            while True:
+                newly, stalled = e.select_b(self.batch, restart, tree_sel)
+                restart = False
+                if newly == 0:
+                    break
+                counts = e.leaf_counts().cpu().numpy().astype(np.int64)
+                slots = np.concatenate([g * e.L + np.arange(prev[g], counts[g]) for g in range(self.G)]).astype(np.int64)
+                prev = counts
+                syms = None
+                if self.use_symmetry:
+                    syms = np.array([self.rngs[g].symmetry() if active[g] else 0 for g in range(self.G)], np.int32)
+                policy, value = self._evaluate(1, slots, model_of_game, syms)
+                e.expand(policy, value, tree_sel)
+                self.sim_count += len(slots)
+                if stalled == 0:
+                    break
+            e.backup_b(self.energy, tree_sel)
+
+    # ------------------------------------------------------------------ run
+    def run(self, exact_rng_order=True):
+        e, G, S, A = self.eng, self.G, self.S, self.A
+        e.reset()
+        e.tree_reset()
+        # choose_first_player (play.py:301-306): cur_model[g] in {0,1} indexes (model1, model2)
+        cur_model = np.array([0 if self.rngs[g].coin() < .5 else 1 for g in range(G)], np.int32)
+        model1_isblack = cur_model == 0
+        # tree index per game: in self-play one shared tree (Q16); else model k searches tree k
+        active = np.ones(G, bool)
+        skipped_last = np.zeros(G, bool)
+        end_reason = np.array(["PLAYED ALL MOVES"] * G, dtype=object)
+        player = np.ones(G, np.int32)               # move_data['player'] (lags one ply, self_play.py:236)
+        moves_rec = [[] for _ in range(G)]
+        temperature = 1
+        for move_n in range(self.num_moves):
+            if not active.any():
+                break
+            if move_n == self.stop_exploration:
+                temperature = 0
+            tree_sel = np.where(active, 0 if self.self_play else cur_model, -1).astype(np.int32)
+            act_idx = np.nonzero(active)[0].astype(np.int64)
+            # root evaluation (self_play.py:187 / nomodel_self_play.py:165)
+            rsyms = None
+            if self.root_symmetry and self.use_symmetry:
+                rsyms = np.zeros(G, np.int32)
+                for g in act_idx:
+                    rsyms[g] = self.rngs[g].symmetry()
+            policy, value = self._evaluate(0, act_idx, cur_model, rsyms)
+            value_h = value.cpu().numpy()
+            # resignation (self_play.py:190-193)
+            thr = np.where(cur_model == 0, self.resign[0], self.resign[1])
+            with np.errstate(invalid='ignore'):
+                resigning = active & ~np.isnan(thr) & (thr != 0) & (value_h <= thr)
+            for g in np.nonzero(resigning)[0]:
+                end_reason[g] = "resign"
+            active = active & ~resigning
+            if not active.any():
+                break
+            tree_sel = np.where(active, 0 if self.self_play else cur_model, -1).astype(np.int32)
+            # new trees only where there is no reusable subtree (self_play.py:195-198)
+            valid = e.tree_valid(tree_sel).cpu().numpy()
+            need = active & (valid == 0)
+            if need.any():
+                noise = None
+                if self.self_play:
+                    noise = np.zeros((G, A), np.float64)
+                    for g in np.nonzero(need)[0]:
+                        noise[g] = self.rngs[g].dirichlet(A)
+                e.tree_new(policy, noise=noise, eps=self.eps, force=False, tree_sel=np.where(need, tree_sel, -1).astype(np.int32))
+            # search
+            if self.mode == 'a':
+                self._search_a(tree_sel, active, cur_model)
+            elif exact_rng_order:
+                self._search_b(tree_sel, active, cur_model)
+            else:
+                self._search_b_fast(tree_sel, active, cur_model)
+            # move pick (self_play.py:138-152)
+            prior, count, _ = e.child_stats(tree_sel, want=("prior", "count"))
+            prior_h = prior.cpu().numpy()
+            forced = None
+            if temperature == 1:
+                count_h = count.cpu().numpy()
+                forced = np.full(G, -1, np.int32)
+                for g in act_idx:
+                    nz = np.nonzero(count_h[g])[0]
+                    total = int(count_h[g].sum())
+                    forced[g] = self.rngs[g].choice([int(m) for m in nz], [int(count_h[g][m]) / float(total) for m in nz])
+            temps = np.full(G, temperature, np.int32)
+            index = e.pick(temps, None, forced, tree_sel).cpu().numpy()
+            if self.record_boards == 'full':
+                boards_h = e.export_boards().cpu().numpy()
+            elif self.record_boards == 'packed':
+                boards_h = e.export_packed(0).cpu().numpy().view(np.uint32)
+            else:
+                boards_h = None
+            apply = np.full(G, -1, np.int32)
+            for g in act_idx:
+                idx = int(index[g])
+                x, y = idx % S, idx // S
+                moves_rec[g].append(dict(
+                    board=None if boards_h is None else (boards_h[g:g + 1].copy() if self.record_boards == 'full' else boards_h[g].copy()),
+                    policy=prior_h[g].copy(), value=value_h[g], move=(x, y), move_n=move_n, player=int(player[g])))
+                if skipped_last[g] and y == S:
+                    end_reason[g] = "BOTH_PASSED"
+                    active[g] = False
+                    continue
+                skipped_last[g] = y == S
+                apply[g] = idx
+            # update trees, play the move, swap sides (self_play.py:223-238)
+            e.reroot(apply)
+            mover = np.where(apply >= 0, self._to_move(), 0)
+            e.apply_moves(apply)
+            moved = apply >= 0
+            player = np.where(moved, mover, player).astype(np.int32)
+            cur_model = np.where(moved, 1 - cur_model, cur_model).astype(np.int32)
+            self.plies_done += int(moved.sum())
+        e.check_errors()
+        return self._finish(model1_isblack, end_reason, player, moves_rec)
+
+    def _to_move(self):
+        # plane 16 of every game (+1 black / -1 white): packed word PW-1
+        pk = self.eng.export_packed(0)
+        return pk[:, -1].cpu().numpy().astype(np.int32)
+
+    def _finish(self, model1_isblack, end_reason, player, moves_rec):
+        e = self.eng
+        sc = e.score().cpu().numpy()
+        ps = {1: "B", 0: "D", -1: "W"}
+        out = []
+        n1, n2 = getattr(self.m1, "name", "model1"), getattr(self.m2, "name", "model2")
+        for g in range(self.G):
+            black, white = float(sc[g, 1]), float(sc[g, 2]) + self.komi
+            winner = 1 if black > white else (0 if black == white else -1)
+            if end_reason[g] == "resign":
+                result = "%s+R" % ps[int(player[g])]
+            else:
+                result = "%s+%s" % (ps[winner], abs(black - white))
+            modelB, modelW = (n1, n2) if model1_isblack[g] else (n2, n1)
+            if winner == 0:
+                winner_model = None
+            elif self.mode == 'a':
+                winner_model = n1 if (winner == 1) == bool(model1_isblack[g]) else n2       # self_play.py:261
+            else:
+                # nomodel_self_play.py:246-249 picks between the B/W names with the same test (reference quirk)
+                winner_model = modelB if (winner == 1) == bool(model1_isblack[g]) else modelW
+            out.append(dict(moves=moves_rec[g], modelB_name=modelB, modelW_name=modelW,
+                            winner={1: 1, -1: 0, 0: None}[winner], winner_model=winner_model, result=result,
+                            resign_model1=None if np.isnan(self.resign[0][g]) else float(self.resign[0][g]),
+                            resign_model2=None if np.isnan(self.resign[1][g]) else float(self.resign[1][g]),
+                            end_reason=str(end_reason[g]), model1_isblack=bool(model1_isblack[g])))
+        return out

@@ -1,0 +1,115 @@
+"""Reference unit tests (test/tests.py, test/tree_util_tests.py) against the CPU oracle."""
+import numpy as np
+import pytest
+
+from oracle import oracle as o
+from tests import ref_cases as rc
+
+
+class OracleApi(object):
+    @staticmethod
+    def game_init():
+        return o.game_init(rc.S)
+
+    make_play = staticmethod(o.make_play)
+    legal_moves = staticmethod(o.legal_moves)
+    get_winner = staticmethod(o.get_winner)
+
+
+@pytest.mark.parametrize("case", rc.RULE_CASES, ids=lambda c: c.__name__)
+def test_rules_case(case):
+    case(OracleApi)
+
+
+def test_capture_group_order():                   # tests.py:137-213 (embedded at the 9x9 corner)
+    def emb(a):
+        b = np.zeros((9, 9), np.int32)
+        a = np.asarray(a)
+        b[:a.shape[0], :a.shape[1]] = a
+        # seal the embedding so the outside is not a liberty
+        return b
+    assert o.capture_group(1, 1, emb([[0, 1, 0], [1, -1, 1], [0, 1, 0]])) == [(1, 1)]
+    b = emb([[0, 1, 0], [1, -1, 1], [1, -1, 1], [0, 1, 0]])
+    assert o.capture_group(1, 1, b) == [(1, 1), (1, 2)]
+    assert o.capture_group(1, 2, b) == [(1, 2), (1, 1)]
+    assert o.capture_group(0, 0, emb([[-1, 1, 0], [1, 0, 0], [0, 0, 0]])) == [(0, 0)]
+    b = emb([[-1, -1, 1], [1, 1, 0], [0, 0, 0]])
+    assert o.capture_group(0, 0, b) == [(0, 0), (1, 0)]
+    assert o.capture_group(1, 0, b) == [(1, 0), (0, 0)]
+    circ = emb([[0, 1, 1, 1, 0], [1, -1, -1, -1, 1], [1, -1, 1, -1, 1], [1, -1, -1, -1, 1], [0, 1, 1, 1, 0]])
+    tgt = [(1, 1), (2, 1), (3, 1), (3, 2), (3, 3), (2, 3), (1, 3), (1, 2)]
+    for x, y in tgt:
+        assert sorted(o.capture_group(x, y, circ)) == sorted(tgt)
+
+
+def test_coloring():                              # tests.py:55-117
+    big = np.array(rc.BIG)
+    tgt = np.array([[1, 1, 1, 2, 0, -2, -1, -1, -1], [1, 1, 1, 2, 0, -2, -1, -1, -1], [1, 1, 1, 2, 0, -2, -1, -1, -1],
+                    [1, 1, 1, 2, -2, -1, -1, -2, -1], [2, 2, 2, -2, -1, -2, -2, -1, -1], [0, 0, 0, 2, -2, 0, 0, -2, -2],
+                    [0, 0, 0, 2, 0, -2, 0, 0, 0], [0, 0, 0, 2, 0, -2, 0, 2, 0], [0, 0, 0, 0, 0, -2, 0, 0, 0]])
+    assert np.array_equal(o.color_board(big, 1) + o.color_board(big, -1), tgt)
+    assert o.get_points(big) == {0: 29, 1: 12, 2: 11, -1: 15, -2: 14}
+
+
+def test_find_best_leaf_order():                  # tree_util_tests.py:69-86
+    tree = {'count': 0, 'mean_value': 0, 'virtual_loss': 0, 'value': 0, 'subtree': {
+        0: {'count': 0, 'p': 1, 'value': 1, 'mean_value': 0, 'virtual_loss': 0, 'subtree': {
+            3: {'count': 0, 'p': 1, 'value': 1, 'mean_value': 0, 'virtual_loss': 0, 'subtree': {}},
+            4: {'count': 0, 'p': 0, 'value': 0, 'mean_value': 0, 'virtual_loss': 0, 'subtree': {}}}},
+        1: {'count': 0, 'p': 0, 'value': 0, 'mean_value': 0, 'virtual_loss': 0, 'subtree': {}}}}
+    t = o.Node.from_dict(tree)
+    n1, m1 = o.find_best_leaf_virtual_loss(t)
+    assert m1 == [0, 3] and n1.virtual_loss > 0
+    n2, m2 = o.find_best_leaf_virtual_loss(t)
+    assert m2 == [0, 4]
+    n3, m3 = o.find_best_leaf_virtual_loss(t)
+    assert m3 == [1] and t.child(0).virtual_loss > 0
+
+
+def test_all_leaf_busy():                         # tree_util_tests.py:88-122
+    tree = {'subtree': {0: {'p': 1, 'value': 1, 'subtree': {}}, 1: {'p': 0, 'subtree': {}}}}
+    t = o.Node.from_dict(tree)
+    o.find_best_leaf_virtual_loss(t)
+    o.find_best_leaf_virtual_loss(t)
+    assert o.find_best_leaf_virtual_loss(t) == (None, None)
+
+
+def _dummy_eval(b):                               # tests.py:34-49 DummyModel: policy ~ [82..1], value +1
+    n = b.shape[0]
+    p = np.tile(np.arange(82, 0, -1, dtype=np.float32), (n, 1))
+    p /= p.sum(axis=1, keepdims=True)
+    return p, np.ones(n, np.float32)
+
+
+def test_mcts_leaf():                             # tests.py:729-744
+    tree = {'subtree': {0: {'p': 1, 'subtree': {}}, 1: {'p': 0, 'subtree': {}}}}
+    t = o.Node.from_dict(tree)
+    board, _ = o.game_init(9)
+    o.simulate(t, board, _dummy_eval, 2, 1)
+    assert t.child(0).count == 1 and t.child(1).count == 1
+    assert t.child(0).value == -1 and t.child(1).value == -1
+    assert t.count == 2 and t.value == -2 and t.mean_value == -1
+
+
+def test_mcts_nested_other_leaves():              # tests.py:1000-1068
+    tree = {'subtree': {0: {'p': .75, 'subtree': {}},
+                        1: {'p': .25, 'subtree': {0: {'p': 1, 'subtree': {}}, 2: {'p': 0, 'subtree': {}}}},
+                        2: {'p': 0, 'subtree': {}}}}
+    t = o.Node.from_dict(tree)
+    board, _ = o.game_init(9)
+    o.simulate(t, board, _dummy_eval, 2, 1)
+    assert t.child(0).count == 1 and t.child(0).value == -1
+    assert t.child(1).value == 1 and t.child(1).count == 1
+    assert t.child(1).child(0).count == 1 and t.child(1).child(0).value == 1 and t.child(1).child(2).count == 0
+    assert t.count == 2 and t.mean_value == 0 and t.child(2).count == 0 and t.child(2).nchild == 0
+    assert t.depth == 4
+
+
+def test_mcts_nested_selected():                  # tests.py:945-998
+    tree = {'subtree': {0: {'p': 1, 'subtree': {1: {'p': 0, 'subtree': {}}, 2: {'p': 1, 'subtree': {}}}},
+                        1: {'p': 0, 'subtree': {}}}}
+    t = o.Node.from_dict(tree)
+    board, _ = o.game_init(9)
+    o.simulate(t, board, _dummy_eval, 2, 1)
+    assert t.child(0).count == 2 and t.child(0).child(1).count == 1 and t.child(0).child(2).count == 1
+    assert t.child(1).count == 0 and t.child(0).value == 2 and t.child(0).mean_value == 1 and t.child(1).value == 0

@@ -34,3 +34,33 @@ def rows_equal(a, b):
             i = int(np.nonzero(a[f] != b[f])[0][0])
             return False, "field %s differs (bitwise) at row %d: %r vs %r" % (f, i, a[i], b[i])
     return True, ""
+
+
+def engine_rows(blocks, meta, p64, A):
+    """Canonical rows from a downloaded engine arena (sejonggo_b200.engine.Engine.download_tree)."""
+    rows = []
+    if not meta['valid']:
+        return np.zeros(0, dtype=ROW_DTYPE)
+
+    def rec(b, depth, f64):
+        blk = blocks[b]
+        for slot in range(A):
+            if not (blk['exist'][slot >> 5] >> (slot & 31)) & 1:
+                continue
+            n = int(blk['n'][slot])
+            w = np.float32(blk['w'][slot])
+            mean = np.float32(w / np.float32(n)) if n > 0 else np.float32(0)
+            p = float(p64[slot]) if f64 else float(blk['prior'][slot])
+            busy = 2 if (blk['busy'][slot >> 5] >> (slot & 31)) & 1 else 0
+            c = int(blk['child'][slot])
+            rows.append((depth, slot, n, w, mean, p, busy, 1 if c >= 0 else 0))
+            if c >= 0:
+                rec(c, depth + 1, False)
+
+    import sys
+    sys.setrecursionlimit(10000)
+    rec(0, 0, bool(meta['root_f64']))
+    a = np.zeros(len(rows), dtype=ROW_DTYPE)
+    for i, r in enumerate(rows):
+        a[i] = r
+    return a
