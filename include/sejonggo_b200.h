@@ -115,6 +115,45 @@ int sgo_tree_upload_sync(sgo_engine *e, int32_t tree, const void *h_blocks, int3
 int sgo_leaf_counts(sgo_engine *e, int32_t *d_counts, void *stream);
 int sgo_tree_valid(sgo_engine *e, const int32_t *d_tree_sel, int32_t *d_valid, void *stream);
 
+/* ---- network: model.py:37-96 (Keras/TF1.7 residual tower; the arithmetic lives in that
+ * third-party dependency, so parity is against an fp32 restatement — DESIGN.md) ---- */
+typedef struct sgo_tower_weights {
+    int32_t n_blocks;          /* conf['N_RESIDUAL_BLOCKS'] */
+    int32_t channels;          /* 256 */
+    int32_t size;              /* board size S; the tower runs on (S-2)x(S-2) after the valid stem conv (Q11) */
+    int32_t reserved;
+    /* all DEVICE pointers; BatchNorm already folded into weights/biases by the host */
+    const float *stem_w;       /* [3][3][17][C]            model.py:57-59 kernel layout (kh,kw,in,out) */
+    const float *stem_b;       /* [C] */
+    const uint16_t *conv_w;    /* bf16 [2*n_blocks][3][3][C out][C in] */
+    const float *conv_b;       /* [2*n_blocks][C] */
+    const float *pol_conv_w;   /* [C][2]                   model.py:73 */
+    const float *pol_conv_b;   /* [2] */
+    const float *pol_fc_w;     /* [2*(S-2)^2][S*S+1]       model.py:80, rows in HWC flatten order */
+    const float *pol_fc_b;     /* [S*S+1] */
+    const float *val_conv_w;   /* [C][2]                   model.py:83 */
+    const float *val_conv_b;   /* [2] */
+    const float *val_fc1_w;    /* [2*(S-2)^2][256]         model.py:90 */
+    const float *val_fc1_b;    /* [256] */
+    const float *val_fc2_w;    /* [256]                    model.py:91 */
+    const float *val_fc2_b;    /* [1] */
+} sgo_tower_weights;
+/* copies the weights into engine-owned HBM and sizes activations for max_positions per forward */
+int sgo_tower_load_weights(sgo_engine *e, int32_t slot, const sgo_tower_weights *w, int32_t max_positions, void *stream);
+int sgo_tower_free(sgo_engine *e, int32_t slot);
+/* model.predict_on_batch (self_play.py:70,187) + symmetry.random_symmetry_predict (symmetry.py:127-132):
+ * n positions taken from games (which=0) or leaf slots (which=1) by d_index (NULL = 0..n-1), per-position
+ * symmetry ids d_sym (NULL = identity); d_policy f32 [..][S*S+1] softmax, d_value f32 [..] tanh; rows are
+ * compact (i) or scattered to d_index[i] when scatter != 0 */
+int sgo_tower_forward(sgo_engine *e, int32_t slot, int32_t which, const int32_t *d_index, int32_t n,
+                      const int32_t *d_sym, int32_t scatter, float *d_policy, float *d_value, void *stream);
+/* sticky tower error flags (16 = an mbarrier wait timed out); synchronises */
+int sgo_tower_check_sync(sgo_engine *e, int32_t slot, int32_t *h_flags, void *stream);
+/* test / profiling hooks: one tensor-core conv layer in isolation; raw activation buffers
+ * bf16 [n*(S-1)+1][S-2][C] (row 0 and every (S-1)-th row are zero padding) */
+int sgo_tower_debug_conv(sgo_engine *e, int32_t slot, int32_t n, int32_t layer, int32_t in, int32_t out, int32_t skip, void *stream);
+int sgo_tower_act_copy(sgo_engine *e, int32_t slot, int32_t buf, int32_t n, void *d_data, int32_t to_tower, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,7 +53,19 @@ _PROTOS = {
     "sgo_tree_upload_sync": [vp, i32, vp, i32, vp, vp],
     "sgo_leaf_counts": [vp, vp, vp],
     "sgo_tree_valid": [vp, vp, vp, vp],
+    "sgo_tower_load_weights": [vp, i32, vp, i32, vp],
+    "sgo_tower_free": [vp, i32],
+    "sgo_tower_forward": [vp, i32, i32, vp, i32, vp, i32, vp, vp, vp],
+    "sgo_tower_check_sync": [vp, i32, C.POINTER(i32), vp],
+    "sgo_tower_debug_conv": [vp, i32, i32, i32, i32, i32, i32, vp],
+    "sgo_tower_act_copy": [vp, i32, i32, i32, vp, i32, vp],
 }
+
+
+class SgoTowerWeights(C.Structure):
+    _fields_ = [("n_blocks", C.c_int32), ("channels", C.c_int32), ("size", C.c_int32), ("reserved", C.c_int32)] + \
+        [(k, C.c_void_p) for k in ("stem_w", "stem_b", "conv_w", "conv_b", "pol_conv_w", "pol_conv_b", "pol_fc_w", "pol_fc_b",
+                                   "val_conv_w", "val_conv_b", "val_fc1_w", "val_fc1_b", "val_fc2_w", "val_fc2_b")]
 
 
 def load(build_if_needed=True):

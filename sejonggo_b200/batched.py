@@ -48,7 +48,7 @@ class HostModelAdapter(object):
         self.model = model
         self.name = getattr(model, "name", "model")
 
-    def evaluate(self, engine, which, idx, syms):
+    def evaluate(self, engine, which, idx, syms, slot=0):
         """idx: int64 device tensor of position indices (games or leaf slots);
         syms: int32 device tensor [len(idx)] or None.  Returns device (policy [k,A], value [k])."""
         k = int(idx.numel())
@@ -104,7 +104,7 @@ class BatchedGames(object):
         self.record_boards = record_boards
         steps = int(self.sims / self.batch)
         if arena_blocks is None:
-            arena_blocks = max(64, 4 * (steps * self.batch + 2))
+            arena_blocks = max(256, 4 * (steps * self.batch + self.batch))
         T = 1 if self_play else 2
         self.eng = engine or Engine(size=size, n_games=n_games, trees_per_game=T, max_leaves=self.batch,
                                     arena_blocks=arena_blocks, komi=komi, device=device)
@@ -138,7 +138,7 @@ class BatchedGames(object):
             if syms_of_game is not None:
                 g = sel // e.L if which else sel
                 syms = torch.as_tensor(syms_of_game[g], dtype=torch.int32, device=e.device)
-            p, v = self.ev[mi].evaluate(e, which, idx, syms)
+            p, v = self.ev[mi].evaluate(e, which, idx, syms, slot=mi)
             policy[idx] = p
             value[idx] = v
             self.eval_count += len(sel)

@@ -4,6 +4,8 @@
 #include "../../include/sejonggo_b200.h"
 #include <string>
 
+struct sgo_tower;
+
 struct sgo_engine {
     sgo_config cfg;
     int S, A, G, T, L, NB;        // size, actions, games, trees/game, leaf slots/game, blocks/arena half
@@ -19,7 +21,7 @@ struct sgo_engine {
     int32_t *err_flags;           // [1] sticky device error bits
     int32_t *counters;            // [4] device scratch counters
     int32_t *h_pinned;            // [8] pinned host mirror
-    void *tower;                  // sgo_tower* (tower.cu)
+    struct sgo_tower *tower[2];   // network weight slots (tower.cu): 0 = model1/best, 1 = model2/tested
     std::string last_error;
 };
 

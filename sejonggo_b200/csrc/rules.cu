@@ -261,7 +261,6 @@ extern "C" int sgo_abi_version(void) { return 1; }
 
 extern "C" const char *sgo_last_error(sgo_engine *e) { return e ? e->last_error.c_str() : "null engine"; }
 
-extern int sgo_tree_init(sgo_engine *e);   // tree.cu
 
 extern "C" int sgo_create(const sgo_config *cfg, sgo_engine **out)
 {
@@ -276,7 +275,7 @@ extern "C" int sgo_create(const sgo_config *cfg, sgo_engine **out)
     e->cfg = *cfg;
     e->S = cfg->size; e->A = cfg->size * cfg->size + 1; e->G = cfg->n_games; e->T = cfg->trees_per_game;
     e->L = cfg->max_leaves; e->NB = cfg->arena_blocks;
-    e->tower = nullptr;
+    e->tower[0] = e->tower[1] = nullptr;
     *out = e;
     SGO_CUDA_OK(e, cudaSetDevice(cfg->device));
     size_t GL = (size_t)e->G * e->L, GT = (size_t)e->G * e->T;
@@ -305,10 +304,14 @@ extern "C" int sgo_create(const sgo_config *cfg, sgo_engine **out)
     return 0;
 }
 
+extern "C" int sgo_tower_free(sgo_engine *e, int32_t slot);
+
 extern "C" int sgo_destroy(sgo_engine *e)
 {
     if (!e) return 0;
     cudaSetDevice(e->cfg.device);
+    sgo_tower_free(e, 0);
+    sgo_tower_free(e, 1);
     cudaFree(e->boards); cudaFree(e->leaf_boards); cudaFree(e->leaf_refs); cudaFree(e->leaf_count);
     cudaFree(e->leaf_masks); cudaFree(e->arena); cudaFree(e->meta); cudaFree(e->root_p64);
     cudaFree(e->wave); cudaFree(e->err_flags); cudaFree(e->counters); cudaFreeHost(e->h_pinned);

@@ -1,0 +1,685 @@
+// tower.cu — the residual policy/value tower of model.py:55-96 on sm_100a.
+//
+//   stem   Conv3x3 "valid" 17->C on the SxS input planes + BN + ReLU (model.py:57-61).
+//          Computed straight from the packed bitboards: input-plane construction
+//          (play.py:295-299) and the symmetry gather (symmetry.py:45-114) are fused in;
+//          no [S,S,17] plane tensor ever touches HBM on this path.
+//   tower  2*N_RESIDUAL_BLOCKS Conv3x3 "same" C->C (+BN folded, +skip, ReLU) as
+//          implicit GEMMs on the 5th-gen tensor cores: TMA (cp.async.bulk.tensor, 128B
+//          swizzle) stages a [RT x W pixels, 64 ch] activation box per filter tap and a
+//          [C x 64] weight box per tap into shared memory, one thread issues
+//          tcgen05.mma (M=128,N=256,K=16, bf16 -> fp32 in TMEM), the epilogue warps read
+//          the accumulators back with tcgen05.ld and fuse bias/skip/ReLU/bf16.
+//   heads  1x1 convs + dense policy (softmax) / value (tanh) heads (model.py:72-92),
+//          fp32, with the "reverse" symmetry policy gather fused into the store.
+//
+// Activation layout in HBM: bf16 [YB][W][C], W = S-2, YB = n_pos*(W+1)+1: every position
+// owns W pixel rows preceded by ONE all-zero pad row (shared top/bottom halo); left/right
+// halos come from TMA out-of-bounds zero fill.  A conv tile = RT consecutive rows (RT*W<=256),
+// so its 9 shifted A operands are plain 3-D TMA boxes at (c0, dx, yb0+dy).
+#include "engine.h"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cstring>
+#include <new>
+
+#define TW_C 256
+#define TW_KCH 64
+#define TW_STAGES 3
+#define TW_TILE_BYTES (256 * 128)
+#define TW_THREADS 192
+#define TW_SPIN_LIMIT (1u << 21)
+
+struct sgo_tower {
+    int n_blocks, S, W, RT, max_pos, YB;
+    int n_layers;
+    float *stem_w, *stem_b;                 // [9][17][C], [C]
+    __nv_bfloat16 *conv_w;                  // [n_layers][9][C co][C ci]
+    float *conv_b;                          // [n_layers][C]
+    float *pol_conv_w, *pol_conv_b, *pol_fc_w, *pol_fc_b;
+    float *val_conv_w, *val_conv_b, *val_fc1_w, *val_fc1_b, *val_fc2_w, *val_fc2_b;
+    __nv_bfloat16 *act[3];                  // [YB][W][C]
+    CUtensorMap map_act[3];
+    CUtensorMap map_w;
+    int32_t *err;
+    int sm_count;
+};
+
+static inline cudaStream_t S_(void *s) { return (cudaStream_t)s; }
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a protocol bug sets an error flag instead of hanging the GPU
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int32_t *err)
+{
+    uint32_t addr = smem_u32(bar);
+    for (uint32_t i = 0; i < TW_SPIN_LIMIT; i++) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    atomicOr(err, 16);
+    return false;
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 | LBO<<16 | SBO<<32 | version=1<<46 | SWIZZLE_128B=2<<61)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
+{
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), K-major both, N>>3 at 17, M>>4 at 24
+#define TW_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24))
+
+struct ConvArgs {
+    int W, RT, rows_per_pos, YB, n_tiles, w_row0, relu;
+    const float *bias;
+    const __nv_bfloat16 *skip;
+    __nv_bfloat16 *out;
+    int32_t *err;
+};
+
+struct ConvSmemTail {
+    uint64_t full[TW_STAGES], empty[TW_STAGES], tmem_full, tmem_empty;
+    uint32_t tmem_base;
+    uint32_t pad;
+    float bias[TW_C];
+};
+#define TW_SMEM_BYTES (TW_STAGES * 2 * TW_TILE_BYTES + (int)sizeof(ConvSmemTail) + 1024)
+
+// One persistent CTA per SM.  warp 0: TMA producer, warp 1: MMA issuer + TMEM owner,
+// warps 2-5: epilogue (warp w reads TMEM lanes 32*(w%4) .. +31).
+__global__ void __launch_bounds__(TW_THREADS, 1)
+k_conv3x3_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w, ConvArgs a)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    ConvSmemTail *tail = reinterpret_cast<ConvSmemTail *>(smem + TW_STAGES * 2 * TW_TILE_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_in) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_w) : "memory");
+        for (int s = 0; s < TW_STAGES; s++) { mbar_init(&tail->full[s], 1); mbar_init(&tail->empty[s], 1); }
+        mbar_init(&tail->tmem_full, 1);
+        mbar_init(&tail->tmem_empty, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tail->tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < TW_C; i += blockDim.x) tail->bias[i] = a.bias[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tail->tmem_base;
+    const uint32_t a_box_bytes = (uint32_t)(TW_KCH * 2 * a.W * a.RT);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < a.n_tiles && ok; tile += gridDim.x) {
+                int yb0 = tile * a.RT;
+                for (int tap = 0; tap < 9 && ok; tap++) {
+                    int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                    for (int kc = 0; kc < TW_C / TW_KCH; kc++) {
+                        ok = mbar_wait(&tail->empty[stage], phase ^ 1, a.err);
+                        if (!ok) break;
+                        uint8_t *sa = smem + (size_t)stage * 2 * TW_TILE_BYTES, *sb = sa + TW_TILE_BYTES;
+                        mbar_expect_tx(&tail->full[stage], a_box_bytes + TW_TILE_BYTES);
+                        tma_load_3d(sa, &map_in, kc * TW_KCH, dx, yb0 + dy, &tail->full[stage]);
+                        tma_load_2d(sb, &map_w, kc * TW_KCH, a.w_row0 + tap * TW_C, &tail->full[stage]);
+                        if (++stage == TW_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, tphase = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < a.n_tiles && ok; tile += gridDim.x) {
+                ok = mbar_wait(&tail->tmem_empty, tphase ^ 1, a.err);      // epilogue drained the accumulators
+                if (!ok) break;
+                tc_fence_after();
+                for (int kb = 0; kb < 9 * (TW_C / TW_KCH); kb++) {
+                    ok = mbar_wait(&tail->full[stage], phase, a.err);
+                    if (!ok) break;
+                    tc_fence_after();
+                    uint32_t sa = smem_u32(smem + (size_t)stage * 2 * TW_TILE_BYTES), sb = sa + TW_TILE_BYTES;
+#pragma unroll
+                    for (int h = 0; h < 2; h++)
+#pragma unroll
+                        for (int k = 0; k < TW_KCH / 16; k++)
+                            umma_bf16(tmem_base + h * 256, umma_desc_sw128(sa + h * (128 * 128) + k * 32),
+                                      umma_desc_sw128(sb + k * 32), TW_IDESC, (kb | k) ? 1u : 0u);
+                    umma_commit(&tail->empty[stage]);                       // frees the smem slot when the MMAs retire
+                    if (++stage == TW_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tail->tmem_full);
+                tphase ^= 1;
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int rr = q * 32 + lane;
+        uint32_t tphase = 0;
+        bool ok = true;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            if (ok) ok = mbar_wait(&tail->tmem_full, tphase, a.err);
+            ok = __all_sync(SGO_FULL, ok);
+            if (!ok) break;
+            tc_fence_after();
+            int yb0 = tile * a.RT;
+#pragma unroll 1
+            for (int h = 0; h < 2; h++) {
+                int r = h * 128 + rr;
+                int ry = r / a.W, x = r - ry * a.W, yb = yb0 + ry;
+                bool valid = r < a.RT * a.W && yb < a.YB && (yb % a.rows_per_pos) != 0;
+                size_t gofs = ((size_t)yb * a.W + x) * TW_C;
+#pragma unroll 1
+                for (int c = 0; c < TW_C / 32; c++) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + h * 256 + c * 32, v);
+                    if (valid) {
+                        uint4 sk[4];
+                        if (a.skip) {
+                            const uint4 *sp = reinterpret_cast<const uint4 *>(a.skip + gofs + c * 32);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) sk[j] = sp[j];
+                        }
+                        uint4 o[4];
+                        uint32_t *ow = reinterpret_cast<uint32_t *>(o);
+                        const uint32_t *sw = reinterpret_cast<const uint32_t *>(sk);
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            float f0 = __uint_as_float(v[2 * j]) + tail->bias[c * 32 + 2 * j];
+                            float f1 = __uint_as_float(v[2 * j + 1]) + tail->bias[c * 32 + 2 * j + 1];
+                            if (a.skip) {
+                                __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162 *>(&sw[j]);
+                                f0 += __bfloat162float(s2.x);
+                                f1 += __bfloat162float(s2.y);
+                            }
+                            if (a.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+                            __nv_bfloat162 p = __floats2bfloat162_rn(f0, f1);
+                            ow[j] = *reinterpret_cast<uint32_t *>(&p);
+                        }
+                        uint4 *op = reinterpret_cast<uint4 *>(a.out + gofs + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) op[j] = o[j];
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tail->tmem_empty);
+            tphase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ stem
+__device__ __forceinline__ void sym_src_t(int S, int sym, int y, int x, int &sy, int &sx)
+{
+    int m = S - 1;
+    switch (sym) {
+    case 0: sy = y; sx = x; break;
+    case 1: sy = x; sx = y; break;
+    case 2: sy = y; sx = m - x; break;
+    case 3: sy = m - y; sx = x; break;
+    case 4: sy = x; sx = m - y; break;
+    case 5: sy = m - y; sx = m - x; break;
+    case 6: sy = m - x; sx = y; break;
+    default: sy = m - x; sx = m - y; break;
+    }
+}
+
+// grid-stride over positions, 256 threads = output channels.  Weights (9*17*C fp32) live in
+// shared memory for the CTA's lifetime; each cell's 16 stone planes are one 16-bit mask.
+__global__ void __launch_bounds__(TW_C, 1)
+k_stem(const Board *boards, const int32_t *index, const int32_t *syms, int n, int S, const float *w, const float *b,
+       __nv_bfloat16 *out)
+{
+    extern __shared__ float sw[];                        // [9][16][C] stone-plane weights
+    __shared__ uint16_t cell[SGO_MAXS * SGO_MAXS];
+    __shared__ int s_tm;
+    const int co = threadIdx.x, W = S - 2;
+    float wtm = 0.f;
+    for (int tap = 0; tap < 9; tap++) {
+        for (int p = 0; p < 16; p++) sw[(tap * 16 + p) * TW_C + co] = w[(tap * 17 + p) * TW_C + co];
+        wtm += w[(tap * 17 + 16) * TW_C + co];            // plane 16 is constant +-1 over the valid window
+    }
+    const float bias = b[co];
+    __syncthreads();
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const Board *bd = boards + (index ? index[i] : i);
+        const int sym = syms ? (syms[i] & 7) : 0;
+        const int tm = bd->to_move, head = bd->head;
+        for (int c = threadIdx.x; c < S * S; c += blockDim.x) {
+            int y = c / S, x = c - y * S, sy, sx;
+            sym_src_t(S, sym, y, x, sy, sx);
+            uint32_t m = 0;
+#pragma unroll
+            for (int k = 0; k < SGO_HIST; k++) {
+                int slot = (head + SGO_HIST - k) & (SGO_HIST - 1);
+                uint32_t bl = (bd->st[slot][0][sy] >> sx) & 1u, wh = (bd->st[slot][1][sy] >> sx) & 1u;
+                uint32_t own = tm == 1 ? bl : wh, opp = tm == 1 ? wh : bl;
+                m |= (own << (2 * k)) | (opp << (2 * k + 1));
+            }
+            cell[c] = (uint16_t)m;
+        }
+        if (threadIdx.x == 0) s_tm = tm;
+        __syncthreads();
+        const float base = bias + (float)s_tm * wtm;
+        const size_t row0 = (size_t)i * (W + 1) + 1;
+        for (int y = 0; y < W; y++)
+            for (int x = 0; x < W; x++) {
+                float acc = base;
+#pragma unroll
+                for (int tap = 0; tap < 9; tap++) {
+                    uint32_t m = cell[(y + tap / 3) * S + x + tap % 3];
+                    while (m) {
+                        int p = __ffs(m) - 1;
+                        m &= m - 1;
+                        acc += sw[(tap * 16 + p) * TW_C + co];
+                    }
+                }
+                out[((row0 + y) * W + x) * TW_C + co] = __float2bfloat16(fmaxf(acc, 0.f));
+            }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ heads
+#define HD_P 4                      // positions per CTA pass (dense weights are read once per pass)
+#define HD_THREADS 256
+
+__device__ __forceinline__ float block_reduce(float v, bool is_max, float *scratch)
+{
+    for (int o = 16; o; o >>= 1) {
+        float t = __shfl_xor_sync(SGO_FULL, v, o);
+        v = is_max ? fmaxf(v, t) : v + t;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = scratch[0];
+    for (int i = 1; i < HD_THREADS / 32; i++) r = is_max ? fmaxf(r, scratch[i]) : r + scratch[i];
+    return r;
+}
+
+struct HeadArgs {
+    int n, S, W, scatter;
+    const int32_t *index, *syms;
+    const __nv_bfloat16 *act;
+    const float *pcw, *pcb, *pfw, *pfb, *vcw, *vcb, *v1w, *v1b, *v2w, *v2b;
+    float *policy, *value;
+};
+
+__global__ void __launch_bounds__(HD_THREADS)
+k_heads(HeadArgs h)
+{
+    extern __shared__ float hs[];
+    const int W = h.W, P = W * W, F = 2 * P, A = h.S * h.S + 1;
+    float *featp = hs;                          // [HD_P][F]
+    float *featv = featp + HD_P * F;            // [HD_P][F]
+    float *logit = featv + HD_P * F;            // [HD_P][A]
+    float *hid = logit + HD_P * A;              // [HD_P][256]
+    float *w4 = hid + HD_P * 256;               // [C][4] 1x1 conv weights (p0,p1,v0,v1)
+    __shared__ float scratch[HD_THREADS / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = threadIdx.x; c < TW_C; c += blockDim.x) {
+        w4[c * 4 + 0] = h.pcw[c * 2]; w4[c * 4 + 1] = h.pcw[c * 2 + 1];
+        w4[c * 4 + 2] = h.vcw[c * 2]; w4[c * 4 + 3] = h.vcw[c * 2 + 1];
+    }
+    __syncthreads();
+    for (int base = blockIdx.x * HD_P; base < h.n; base += gridDim.x * HD_P) {
+        int np = min(HD_P, h.n - base);
+        // 1x1 convs + BN(folded) + ReLU: one warp per pixel, lanes split the 256 channels
+        for (int t = warp; t < np * P; t += HD_THREADS / 32) {
+            int pi = t / P, pix = t - pi * P, y = pix / W, x = pix - y * W;
+            size_t row = (size_t)(base + pi) * (W + 1) + 1 + y;
+            const uint4 *ap = reinterpret_cast<const uint4 *>(h.act + (row * W + x) * TW_C) + lane;
+            uint4 raw = *ap;
+            const __nv_bfloat162 *a2 = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+            float s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float f0 = __bfloat162float(a2[j].x), f1 = __bfloat162float(a2[j].y);
+                const float *wa = w4 + (lane * 8 + 2 * j) * 4;
+                s0 = fmaf(f0, wa[0], s0); s1 = fmaf(f0, wa[1], s1); s2 = fmaf(f0, wa[2], s2); s3 = fmaf(f0, wa[3], s3);
+                s0 = fmaf(f1, wa[4], s0); s1 = fmaf(f1, wa[5], s1); s2 = fmaf(f1, wa[6], s2); s3 = fmaf(f1, wa[7], s3);
+            }
+            for (int o = 16; o; o >>= 1) {
+                s0 += __shfl_xor_sync(SGO_FULL, s0, o); s1 += __shfl_xor_sync(SGO_FULL, s1, o);
+                s2 += __shfl_xor_sync(SGO_FULL, s2, o); s3 += __shfl_xor_sync(SGO_FULL, s3, o);
+            }
+            if (lane == 0) {
+                featp[pi * F + pix * 2 + 0] = fmaxf(s0 + h.pcb[0], 0.f);      // flatten order HWC (model.py:77-79)
+                featp[pi * F + pix * 2 + 1] = fmaxf(s1 + h.pcb[1], 0.f);
+                featv[pi * F + pix * 2 + 0] = fmaxf(s2 + h.vcb[0], 0.f);
+                featv[pi * F + pix * 2 + 1] = fmaxf(s3 + h.vcb[1], 0.f);
+            }
+        }
+        __syncthreads();
+        // policy dense F -> A (thread per action), value dense F -> 256 (thread per unit)
+        for (int a0 = threadIdx.x; a0 < A; a0 += blockDim.x) {
+            float acc[HD_P];
+#pragma unroll
+            for (int p = 0; p < HD_P; p++) acc[p] = h.pfb[a0];
+            for (int i = 0; i < F; i++) {
+                float wv = h.pfw[(size_t)i * A + a0];
+#pragma unroll
+                for (int p = 0; p < HD_P; p++) acc[p] = fmaf(featp[p * F + i], wv, acc[p]);
+            }
+#pragma unroll
+            for (int p = 0; p < HD_P; p++) logit[p * A + a0] = acc[p];
+        }
+        {
+            int j = threadIdx.x;
+            float acc[HD_P];
+#pragma unroll
+            for (int p = 0; p < HD_P; p++) acc[p] = h.v1b[j];
+            for (int i = 0; i < F; i++) {
+                float wv = h.v1w[(size_t)i * 256 + j];
+#pragma unroll
+                for (int p = 0; p < HD_P; p++) acc[p] = fmaf(featv[p * F + i], wv, acc[p]);
+            }
+#pragma unroll
+            for (int p = 0; p < HD_P; p++) hid[p * 256 + j] = fmaxf(acc[p], 0.f) * h.v2w[j];
+        }
+        __syncthreads();
+        for (int p = 0; p < np; p++) {
+            float mx = -3.4e38f;
+            for (int a0 = threadIdx.x; a0 < A; a0 += blockDim.x) mx = fmaxf(mx, logit[p * A + a0]);
+            mx = block_reduce(mx, true, scratch);
+            float sum = 0.f;
+            for (int a0 = threadIdx.x; a0 < A; a0 += blockDim.x) {
+                float e = expf(logit[p * A + a0] - mx);
+                logit[p * A + a0] = e;
+                sum += e;
+            }
+            sum = block_reduce(sum, false, scratch);
+            float vs = block_reduce(hid[p * 256 + threadIdx.x], false, scratch);
+            int i = base + p;
+            size_t orow = h.scatter ? (size_t)(h.index ? h.index[i] : i) : (size_t)i;
+            int sym = h.syms ? (h.syms[i] & 7) : 0;
+            float inv = 1.f / sum;
+            for (int a0 = threadIdx.x; a0 < A; a0 += blockDim.x) {
+                int src = a0;
+                if (a0 < h.S * h.S) {                       // "reverse" gather re-uses the forward map (Q8)
+                    int y = a0 / h.S, x = a0 - y * h.S, sy, sx;
+                    sym_src_t(h.S, sym, y, x, sy, sx);
+                    src = sy * h.S + sx;
+                }
+                h.policy[orow * A + a0] = logit[p * A + src] * inv;
+            }
+            if (threadIdx.x == 0) h.value[orow] = tanhf(vs + h.v2b[0]);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+static int make_maps(sgo_engine *e, sgo_tower *t)
+{
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return sgo_fail(e, "cuTensorMapEncodeTiled unavailable");
+    for (int i = 0; i < 3; i++) {
+        cuuint64_t dims[3] = {(cuuint64_t)TW_C, (cuuint64_t)t->W, (cuuint64_t)t->YB};
+        cuuint64_t strides[2] = {(cuuint64_t)TW_C * 2, (cuuint64_t)TW_C * 2 * t->W};
+        cuuint32_t box[3] = {TW_KCH, (cuuint32_t)t->W, (cuuint32_t)t->RT};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&t->map_act[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, t->act[i], dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(activations) failed");
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)TW_C, (cuuint64_t)t->n_layers * 9 * TW_C};
+    cuuint64_t strides[1] = {(cuuint64_t)TW_C * 2};
+    cuuint32_t box[2] = {TW_KCH, TW_C};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&t->map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, t->conv_w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(weights) failed");
+    return 0;
+}
+
+static void tower_free(sgo_tower *t)
+{
+    if (!t) return;
+    cudaFree(t->stem_w); cudaFree(t->stem_b); cudaFree(t->conv_w); cudaFree(t->conv_b);
+    cudaFree(t->pol_conv_w); cudaFree(t->pol_conv_b); cudaFree(t->pol_fc_w); cudaFree(t->pol_fc_b);
+    cudaFree(t->val_conv_w); cudaFree(t->val_conv_b); cudaFree(t->val_fc1_w); cudaFree(t->val_fc1_b);
+    cudaFree(t->val_fc2_w); cudaFree(t->val_fc2_b);
+    for (int i = 0; i < 3; i++) cudaFree(t->act[i]);
+    cudaFree(t->err);
+    delete t;
+}
+
+extern "C" int sgo_tower_free(sgo_engine *e, int32_t slot)
+{
+    if (slot < 0 || slot > 1) return sgo_fail(e, "tower slot must be 0 or 1");
+    tower_free(e->tower[slot]);
+    e->tower[slot] = nullptr;
+    return 0;
+}
+
+#define DUP(dst, src, count, type)                                                                     \
+    do {                                                                                               \
+        SGO_CUDA_OK(e, cudaMalloc(&(dst), sizeof(type) * (size_t)(count)));                            \
+        SGO_CUDA_OK(e, cudaMemcpyAsync((dst), (src), sizeof(type) * (size_t)(count), cudaMemcpyDeviceToDevice, S_(stream))); \
+    } while (0)
+
+extern "C" int sgo_tower_load_weights(sgo_engine *e, int32_t slot, const sgo_tower_weights *w, int32_t max_positions, void *stream)
+{
+    if (slot < 0 || slot > 1) return sgo_fail(e, "tower slot must be 0 or 1");
+    if (w->channels != TW_C) return sgo_fail(e, "tower kernels are built for 256 channels");
+    if (w->size != e->S || e->S < 5) return sgo_fail(e, "tower board size mismatch (needs S >= 5)");
+    if (max_positions < 1) return sgo_fail(e, "max_positions must be positive");
+    sgo_tower_free(e, slot);
+    sgo_tower *t = new (std::nothrow) sgo_tower();
+    if (!t) return sgo_fail(e, "out of host memory");
+    memset(t, 0, sizeof(*t));
+    e->tower[slot] = t;
+    t->n_blocks = w->n_blocks; t->n_layers = 2 * w->n_blocks; t->S = e->S; t->W = e->S - 2;
+    t->RT = 256 / t->W; if (t->RT > 256) t->RT = 256;
+    t->max_pos = max_positions;
+    t->YB = max_positions * (t->W + 1) + 1;
+    int P = t->W * t->W, A = e->A;
+    DUP(t->stem_w, w->stem_w, 9 * 17 * TW_C, float);
+    DUP(t->stem_b, w->stem_b, TW_C, float);
+    DUP(t->conv_w, (const __nv_bfloat16 *)w->conv_w, (size_t)t->n_layers * 9 * TW_C * TW_C, __nv_bfloat16);
+    DUP(t->conv_b, w->conv_b, t->n_layers * TW_C, float);
+    DUP(t->pol_conv_w, w->pol_conv_w, TW_C * 2, float);
+    DUP(t->pol_conv_b, w->pol_conv_b, 2, float);
+    DUP(t->pol_fc_w, w->pol_fc_w, (size_t)2 * P * A, float);
+    DUP(t->pol_fc_b, w->pol_fc_b, A, float);
+    DUP(t->val_conv_w, w->val_conv_w, TW_C * 2, float);
+    DUP(t->val_conv_b, w->val_conv_b, 2, float);
+    DUP(t->val_fc1_w, w->val_fc1_w, (size_t)2 * P * 256, float);
+    DUP(t->val_fc1_b, w->val_fc1_b, 256, float);
+    DUP(t->val_fc2_w, w->val_fc2_w, 256, float);
+    DUP(t->val_fc2_b, w->val_fc2_b, 1, float);
+    size_t act_bytes = (size_t)t->YB * t->W * TW_C * sizeof(__nv_bfloat16);
+    for (int i = 0; i < 3; i++) {
+        SGO_CUDA_OK(e, cudaMalloc(&t->act[i], act_bytes));
+        SGO_CUDA_OK(e, cudaMemsetAsync(t->act[i], 0, act_bytes, S_(stream)));     // pad rows stay zero forever
+    }
+    SGO_CUDA_OK(e, cudaMalloc(&t->err, sizeof(int32_t)));
+    SGO_CUDA_OK(e, cudaMemsetAsync(t->err, 0, sizeof(int32_t), S_(stream)));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    SGO_CUDA_OK(e, cudaFuncSetAttribute(k_conv3x3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM_BYTES));
+    SGO_CUDA_OK(e, cudaFuncSetAttribute(k_stem, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 16 * TW_C * (int)sizeof(float)));
+    int hs = (HD_P * (4 * P + A + 256) + TW_C * 4) * (int)sizeof(float);
+    SGO_CUDA_OK(e, cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, hs));
+    int rc = make_maps(e, t);
+    if (rc) return rc;
+    SGO_CUDA_OK(e, cudaStreamSynchronize(S_(stream)));
+    return 0;
+}
+
+static int launch_conv(sgo_engine *e, sgo_tower *t, int n, int layer, int in, int out, int skip, void *stream)
+{
+    ConvArgs a;
+    a.W = t->W; a.RT = t->RT; a.rows_per_pos = t->W + 1;
+    a.YB = n * (t->W + 1) + 1;
+    a.n_tiles = (a.YB + t->RT - 1) / t->RT;
+    a.w_row0 = layer * 9 * TW_C;
+    a.relu = 1;
+    a.bias = t->conv_b + (size_t)layer * TW_C;
+    a.skip = skip >= 0 ? t->act[skip] : nullptr;
+    a.out = t->act[out];
+    a.err = t->err;
+    int grid = a.n_tiles < t->sm_count ? a.n_tiles : t->sm_count;
+    k_conv3x3_tc<<<grid, TW_THREADS, TW_SMEM_BYTES, S_(stream)>>>(t->map_act[in], t->map_w, a);
+    SGO_CUDA_OK(e, cudaGetLastError());
+    return 0;
+}
+
+// model.predict_on_batch for n positions (games: which=0, leaf slots: which=1) gathered by
+// d_index (NULL = 0..n-1), symmetry ids d_sym per position (NULL = identity).  Outputs are
+// compact [n] rows, or scattered to row d_index[i] when scatter != 0.
+extern "C" int sgo_tower_forward(sgo_engine *e, int32_t slot, int32_t which, const int32_t *d_index, int32_t n,
+                                 const int32_t *d_sym, int32_t scatter, float *d_policy, float *d_value, void *stream)
+{
+    if (slot < 0 || slot > 1 || !e->tower[slot]) return sgo_fail(e, "tower slot has no weights");
+    sgo_tower *t = e->tower[slot];
+    if (n < 0 || n > t->max_pos) return sgo_fail(e, "n exceeds the tower's max_positions");
+    if (n == 0) return 0;
+    const Board *boards = which ? e->leaf_boards : e->boards;
+    int P = t->W * t->W;
+    int grid = n < t->sm_count ? n : t->sm_count;
+    k_stem<<<grid, TW_C, 9 * 16 * TW_C * sizeof(float), S_(stream)>>>(boards, d_index, d_sym, n, t->S, t->stem_w, t->stem_b, t->act[0]);
+    SGO_CUDA_OK(e, cudaGetLastError());
+    int x = 0;                                     // act[x] holds the block input
+    for (int b = 0; b < t->n_blocks; b++) {
+        int tmp = (x + 1) % 3, y = (x + 2) % 3;
+        int rc = launch_conv(e, t, n, 2 * b, x, tmp, -1, stream);           // conv1 + BN + ReLU   (model.py:39-41)
+        if (rc) return rc;
+        rc = launch_conv(e, t, n, 2 * b + 1, tmp, y, x, stream);            // conv2 + BN + skip + ReLU (model.py:42-45)
+        if (rc) return rc;
+        x = y;
+    }
+    HeadArgs h;
+    h.n = n; h.S = t->S; h.W = t->W; h.scatter = scatter; h.index = d_index; h.syms = d_sym; h.act = t->act[x];
+    h.pcw = t->pol_conv_w; h.pcb = t->pol_conv_b; h.pfw = t->pol_fc_w; h.pfb = t->pol_fc_b;
+    h.vcw = t->val_conv_w; h.vcb = t->val_conv_b; h.v1w = t->val_fc1_w; h.v1b = t->val_fc1_b;
+    h.v2w = t->val_fc2_w; h.v2b = t->val_fc2_b; h.policy = d_policy; h.value = d_value;
+    int hs = (HD_P * (4 * P + e->A + 256) + TW_C * 4) * (int)sizeof(float);
+    int hgrid = (n + HD_P - 1) / HD_P;
+    if (hgrid > 4 * t->sm_count) hgrid = 4 * t->sm_count;
+    k_heads<<<hgrid, HD_THREADS, hs, S_(stream)>>>(h);
+    SGO_CUDA_OK(e, cudaGetLastError());
+    return 0;
+}
+
+// debugging / parity hook: copy the activations after `layer` convs... kept minimal: returns
+// the sticky tower error flag (bit 16 = mbarrier wait timed out) and clears it.
+extern "C" int sgo_tower_check_sync(sgo_engine *e, int32_t slot, int32_t *h_flags, void *stream)
+{
+    if (slot < 0 || slot > 1 || !e->tower[slot]) return sgo_fail(e, "tower slot has no weights");
+    SGO_CUDA_OK(e, cudaMemcpyAsync(e->h_pinned + 6, e->tower[slot]->err, sizeof(int32_t), cudaMemcpyDeviceToHost, S_(stream)));
+    SGO_CUDA_OK(e, cudaMemsetAsync(e->tower[slot]->err, 0, sizeof(int32_t), S_(stream)));
+    SGO_CUDA_OK(e, cudaStreamSynchronize(S_(stream)));
+    if (h_flags) *h_flags = e->h_pinned[6];
+    return 0;
+}
+
+// tensor-core conv in isolation (tests / profiling): runs conv layer `layer` from act[in] to act[out]
+extern "C" int sgo_tower_debug_conv(sgo_engine *e, int32_t slot, int32_t n, int32_t layer, int32_t in, int32_t out, int32_t skip, void *stream)
+{
+    if (slot < 0 || slot > 1 || !e->tower[slot]) return sgo_fail(e, "tower slot has no weights");
+    sgo_tower *t = e->tower[slot];
+    if (n < 1 || n > t->max_pos || layer < 0 || layer >= t->n_layers || in < 0 || in > 2 || out < 0 || out > 2 || skip > 2)
+        return sgo_fail(e, "debug_conv arguments out of range");
+    return launch_conv(e, t, n, layer, in, out, skip, stream);
+}
+
+// raw activation buffer access (bf16 [n*(W+1)+1][W][C]) for tests
+extern "C" int sgo_tower_act_copy(sgo_engine *e, int32_t slot, int32_t buf, int32_t n, void *d_data, int32_t to_tower, void *stream)
+{
+    if (slot < 0 || slot > 1 || !e->tower[slot]) return sgo_fail(e, "tower slot has no weights");
+    sgo_tower *t = e->tower[slot];
+    if (buf < 0 || buf > 2 || n < 1 || n > t->max_pos) return sgo_fail(e, "act_copy arguments out of range");
+    size_t bytes = ((size_t)n * (t->W + 1) + 1) * t->W * TW_C * sizeof(__nv_bfloat16);
+    if (to_tower) SGO_CUDA_OK(e, cudaMemcpyAsync(t->act[buf], d_data, bytes, cudaMemcpyDeviceToDevice, S_(stream)));
+    else SGO_CUDA_OK(e, cudaMemcpyAsync(d_data, t->act[buf], bytes, cudaMemcpyDeviceToDevice, S_(stream)));
+    return 0;
+}

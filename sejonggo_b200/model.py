@@ -1,0 +1,175 @@
+"""The evaluator: model.py:55-96's residual policy/value tower as a GPU-resident object.
+
+`TowerModel` satisfies the reference's duck-typed model protocol
+(`.name`, `.predict_on_batch(X[n,S,S,17]) -> (policy[n,S*S+1], value[n,1])`,
+self_play.py:70,187; symmetry.py:130) for legacy callers and parity tests, and the
+engine-side protocol (`.evaluate(engine, which, idx, syms, slot)`) that keeps
+boards, activations and outputs in HBM.  Weight I/O in Keras .h5 is out of scope
+(SURVEY §2 row 6); weights come from `init_params` (Keras-2.2.2 default
+initialisers: glorot-uniform kernels, zero biases, BN gamma=1 beta=0 mean=0 var=1)
+or from a dict in the same layout.
+"""
+import ctypes as C
+import math
+import numpy as np
+import torch
+
+from . import _abi
+from .conf import conf
+from .engine import Engine, EngineError
+
+BN_EPS = 1e-3
+CHANNELS = 256
+
+
+def _glorot(gen, shape, fan_in, fan_out):
+    limit = math.sqrt(6.0 / (fan_in + fan_out))
+    return (torch.rand(shape, generator=gen, dtype=torch.float32) * 2 - 1) * limit
+
+
+def _bn_default(c):
+    return dict(gamma=torch.ones(c), beta=torch.zeros(c), mean=torch.zeros(c), var=torch.ones(c))
+
+
+def _bn_random(gen, c):
+    return dict(gamma=0.5 + torch.rand(c, generator=gen), beta=0.2 * torch.randn(c, generator=gen),
+                mean=0.2 * torch.randn(c, generator=gen), var=0.5 + torch.rand(c, generator=gen))
+
+
+def init_params(size=None, n_blocks=None, seed=0, randomize_bn=False, random_bias=False):
+    """Random-init parameters in the reference's Keras layout (model.py:55-96)."""
+    size = size or conf['SIZE']
+    n_blocks = conf['N_RESIDUAL_BLOCKS'] if n_blocks is None else n_blocks
+    g = torch.Generator().manual_seed(seed)
+    C_, W = CHANNELS, size - 2
+    bn = (lambda c: _bn_random(g, c)) if randomize_bn else _bn_default
+    bias = (lambda c: 0.1 * torch.randn(c, generator=g)) if random_bias else (lambda c: torch.zeros(c))
+    p = {'meta': dict(size=size, n_blocks=n_blocks, seed=seed)}
+    p['stem_k'] = _glorot(g, (3, 3, 17, C_), 9 * 17, 9 * C_)
+    p['stem_b'] = bias(C_)
+    p['stem_bn'] = bn(C_)
+    for i in range(n_blocks):
+        for j in (1, 2):
+            p['res%d_k%d' % (i, j)] = _glorot(g, (3, 3, C_, C_), 9 * C_, 9 * C_)
+            p['res%d_b%d' % (i, j)] = bias(C_)
+            p['res%d_bn%d' % (i, j)] = bn(C_)
+    F = 2 * W * W
+    A = size * size + 1
+    p['pol_k'] = _glorot(g, (1, 1, C_, 2), C_, 2); p['pol_b'] = bias(2); p['pol_bn'] = bn(2)
+    p['pol_fc_w'] = _glorot(g, (F, A), F, A); p['pol_fc_b'] = bias(A)
+    p['val_k'] = _glorot(g, (1, 1, C_, 2), C_, 2); p['val_b'] = bias(2); p['val_bn'] = bn(2)
+    p['val_fc1_w'] = _glorot(g, (F, 256), F, 256); p['val_fc1_b'] = bias(256)
+    p['val_fc2_w'] = _glorot(g, (256, 1), 256, 1); p['val_fc2_b'] = bias(1)
+    return p
+
+
+def n_params(p):
+    """Parameter count the way Keras reports it (BN has 4 vectors per channel)."""
+    t = 0
+    for k, v in p.items():
+        if k == 'meta':
+            continue
+        t += sum(x.numel() for x in v.values()) if isinstance(v, dict) else v.numel()
+    return t
+
+
+def fold_bn(k, b, bn):
+    """conv/dense followed by inference BatchNorm -> one affine op (fp32)."""
+    s = bn['gamma'] / torch.sqrt(bn['var'] + BN_EPS)
+    return k * s.view(*([1] * (k.dim() - 1)), -1), (b - bn['mean']) * s + bn['beta']
+
+
+def folded_arrays(p):
+    """Tensors in the layout sgo_tower_weights expects (include/sejonggo_b200.h)."""
+    nb = p['meta']['n_blocks']
+    out = {}
+    k, b = fold_bn(p['stem_k'], p['stem_b'], p['stem_bn'])
+    out['stem_w'], out['stem_b'] = k.contiguous(), b.contiguous()
+    ws, bs = [], []
+    for i in range(nb):
+        for j in (1, 2):
+            k, b = fold_bn(p['res%d_k%d' % (i, j)], p['res%d_b%d' % (i, j)], p['res%d_bn%d' % (i, j)])
+            ws.append(k.permute(0, 1, 3, 2).contiguous())          # (kh,kw,in,out) -> (kh,kw,out,in)
+            bs.append(b)
+    out['conv_w'] = torch.stack(ws).to(torch.bfloat16).contiguous() if ws else torch.zeros((0,), dtype=torch.bfloat16)
+    out['conv_b'] = torch.stack(bs).contiguous() if bs else torch.zeros((0,))
+    k, b = fold_bn(p['pol_k'], p['pol_b'], p['pol_bn'])
+    out['pol_conv_w'], out['pol_conv_b'] = k.reshape(CHANNELS, 2).contiguous(), b.contiguous()
+    out['pol_fc_w'], out['pol_fc_b'] = p['pol_fc_w'].contiguous(), p['pol_fc_b'].contiguous()
+    k, b = fold_bn(p['val_k'], p['val_b'], p['val_bn'])
+    out['val_conv_w'], out['val_conv_b'] = k.reshape(CHANNELS, 2).contiguous(), b.contiguous()
+    out['val_fc1_w'], out['val_fc1_b'] = p['val_fc1_w'].contiguous(), p['val_fc1_b'].contiguous()
+    out['val_fc2_w'], out['val_fc2_b'] = p['val_fc2_w'].reshape(256).contiguous(), p['val_fc2_b'].contiguous()
+    return out
+
+
+class TowerModel(object):
+    is_sgo_evaluator = True
+
+    def __init__(self, name="model_1", params=None, size=None, n_blocks=None, seed=0, max_positions=8192):
+        self.name = name
+        self.params = params if params is not None else init_params(size, n_blocks, seed)
+        self.size = self.params['meta']['size']
+        self.max_positions = max_positions
+        self._folded = None
+        self._loaded = {}            # id(engine) -> slot
+        self._host_engine = None
+
+    # ---- engine-side protocol ----------------------------------------------------
+    def attach(self, engine, slot=0, max_positions=None):
+        key = (id(engine), slot)
+        if self._loaded.get(key):
+            return
+        if engine.S != self.size:
+            raise EngineError("model is for %dx%d boards, engine is %dx%d" % (self.size, self.size, engine.S, engine.S))
+        if self._folded is None:
+            self._folded = folded_arrays(self.params)
+        dev = {k: v.to(engine.device) for k, v in self._folded.items()}
+        w = _abi.SgoTowerWeights(n_blocks=self.params['meta']['n_blocks'], channels=CHANNELS, size=self.size)
+        for k, v in dev.items():
+            setattr(w, k, v.data_ptr())
+        mp = max_positions or self.max_positions
+        engine._ck(engine.lib.sgo_tower_load_weights(engine.h, slot, C.byref(w), int(mp), engine._stream()))
+        self._loaded[key] = mp
+        torch.cuda.synchronize(engine.device)
+
+    def evaluate(self, engine, which, idx, syms=None, slot=0, out=None):
+        """idx int64/int32 device tensor of positions (games / leaf slots); returns compact
+        device tensors (policy [k,A] f32, value [k] f32)."""
+        self.attach(engine, slot)
+        mp = self._loaded[(id(engine), slot)]
+        k = int(idx.numel())
+        idx32 = idx.to(torch.int32).contiguous()
+        sy = None if syms is None else syms.to(torch.int32).contiguous()
+        policy = torch.empty((k, engine.A), dtype=torch.float32, device=engine.device)
+        value = torch.empty((k,), dtype=torch.float32, device=engine.device)
+        for s in range(0, k, mp):
+            n = min(mp, k - s)
+            engine._ck(engine.lib.sgo_tower_forward(
+                engine.h, slot, which, C.c_void_p(idx32[s:].data_ptr()), n,
+                C.c_void_p(0 if sy is None else sy[s:].data_ptr()), 0,
+                C.c_void_p(policy[s:].data_ptr()), C.c_void_p(value[s:].data_ptr()), engine._stream()))
+        return policy, value
+
+    def check(self, engine, slot=0):
+        f = C.c_int32(0)
+        engine._ck(engine.lib.sgo_tower_check_sync(engine.h, slot, C.byref(f), engine._stream()))
+        if f.value:
+            raise EngineError("tower kernel error flags 0x%x (16 = mbarrier wait timed out)" % f.value)
+
+    # ---- reference protocol (self_play.py:70,187) ----------------------------------
+    def predict_on_batch(self, X):
+        X = np.asarray(X)
+        n = X.shape[0]
+        if self._host_engine is None or self._host_engine.G < n:
+            self._host_engine = Engine(size=self.size, n_games=max(n, 64), trees_per_game=1, max_leaves=1, arena_blocks=2)
+        e = self._host_engine
+        e.import_boards(X.astype(np.int32))
+        idx = torch.arange(n, dtype=torch.int32, device=e.device)
+        p, v = self.evaluate(e, 0, idx, None, slot=0)
+        return p.cpu().numpy(), v.cpu().numpy().reshape(n, 1)
+
+
+def build_model(name, size=None, n_blocks=None, seed=0):
+    """model.py:55 build_model: a random-init tower with the reference's architecture."""
+    return TowerModel(name, size=size, n_blocks=n_blocks, seed=seed)

@@ -79,7 +79,7 @@ def test_mcts_fixture(name):
     A = S * S + 1
     ev = lambda b: evaluate(b, seed, True)
     G = 3                                            # the same game three times: batch independence
-    e = _engine(size=S, n_games=G, trees_per_game=1, max_leaves=batch, arena_blocks=4 * steps * batch + 8)
+    e = _engine(size=S, n_games=G, trees_per_game=1, max_leaves=batch, arena_blocks=max(2048, 8 * steps * batch))
     e.reset()
     e.tree_reset()
     pol, _ = eval_slots(e, 0, np.arange(G), ev)
@@ -96,6 +96,7 @@ def test_mcts_fixture(name):
             blocks, meta, p64 = e.download_tree(g)
             ok, why = rows_equal(engine_rows(blocks, meta, p64, A), z["trees"][offs[ply]:offs[ply + 1]])
             assert ok, "ply %d game %d: %s" % (ply, g, why)
+        e.check_errors()
         t0 = e.pick(np.zeros(G, np.int32)).cpu().numpy()
         assert (t0 == z["t0picks"][ply]).all()
         sel = int(z["picks"][ply])
@@ -120,7 +121,7 @@ def test_mcts_vs_oracle_with_symmetries(mode, S, batch, steps, plies):
     engine vs C oracle tree-for-tree."""
     A, G = S * S + 1, 4
     rs = np.random.RandomState(100 + S + batch)
-    e = _engine(size=S, n_games=G, trees_per_game=1, max_leaves=batch, arena_blocks=4 * steps * batch + 8)
+    e = _engine(size=S, n_games=G, trees_per_game=1, max_leaves=batch, arena_blocks=max(2048, 8 * steps * batch))
     e.reset()
     e.tree_reset()
     salts = [7 * g + 1 for g in range(G)]
@@ -190,6 +191,7 @@ def test_mcts_vs_oracle_with_symmetries(mode, S, batch, steps, plies):
                         break
                 e.backup_b(batch)
         picks = np.zeros(G, np.int32)
+        e.check_errors()
         for g in range(G):
             blocks, meta, p64 = e.download_tree(g)
             ok, why = rows_equal(engine_rows(blocks, meta, p64, A), oracle_rows(ots[g]))

@@ -1,0 +1,140 @@
+"""GPU parity of the tower kernels (csrc/tower.cu) against the fp32 torch restatement of
+model.py:55-96 (oracle/tower_ref.py).  Tolerance: 1e-2 absolute on policy and value, the
+figure BASELINE.json's north_star states for bf16 compute."""
+import ctypes as C
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as o
+from oracle import tower_ref
+from tests.conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+def _positions(size, n, seed):
+    """Plausible mid-game positions: random legal playouts from the oracle."""
+    rs = np.random.RandomState(seed)
+    boards = []
+    for i in range(n):
+        b, _ = o.game_init(size)
+        for t in range(int(rs.randint(0, size * size // 2))):
+            legal = np.nonzero(o.legal_moves(b)[:-1] == 0)[0]
+            mv = size * size if len(legal) == 0 or rs.rand() < 0.05 else int(rs.choice(legal))
+            o.make_play(mv % size, mv // size, b)
+        boards.append(b)
+    return np.concatenate(boards)
+
+
+def test_conv_layer_in_isolation():
+    """One tcgen05 conv layer (+bias, +skip, ReLU) vs torch conv2d on the same bf16 data."""
+    from sejonggo_b200.engine import Engine
+    from sejonggo_b200 import model
+    S, n = 19, 37                                   # 37 positions: tiles straddle position boundaries, ragged last tile
+    W = S - 2
+    params = model.init_params(S, 1, seed=3, randomize_bn=True, random_bias=True)
+    m = model.TowerModel("t", params=params, max_positions=64)
+    e = Engine(size=S, n_games=64, max_leaves=1, arena_blocks=2)
+    m.attach(e, 0)
+    g = torch.Generator().manual_seed(1)
+    rows = n * (W + 1) + 1
+    x = torch.randn((n, W, W, 256), generator=g).clamp_(-3, 3)
+    skip = torch.randn((n, W, W, 256), generator=g)
+
+    def to_padded(t):
+        buf = torch.zeros((rows, W, 256), dtype=torch.bfloat16)
+        buf[1:].view(n, W + 1, W, 256)[:, :W] = t.to(torch.bfloat16)
+        return buf.cuda()
+
+    def from_padded(buf):
+        return buf.cpu()[1:].view(n, W + 1, W, 256)[:, :W].float()
+
+    f = model.folded_arrays(params)
+    for layer, use_skip in ((0, False), (1, True)):
+        e._ck(e.lib.sgo_tower_act_copy(e.h, 0, 0, n, C.c_void_p(to_padded(x).data_ptr()), 1, e._stream()))
+        e._ck(e.lib.sgo_tower_act_copy(e.h, 0, 2, n, C.c_void_p(to_padded(skip).data_ptr()), 1, e._stream()))
+        e._ck(e.lib.sgo_tower_debug_conv(e.h, 0, n, layer, 0, 1, 2 if use_skip else -1, e._stream()))
+        out = torch.empty((rows, W, 256), dtype=torch.bfloat16, device="cuda")
+        e._ck(e.lib.sgo_tower_act_copy(e.h, 0, 1, n, C.c_void_p(out.data_ptr()), 0, e._stream()))
+        torch.cuda.synchronize()
+        m.check(e, 0)
+        got = from_padded(out)
+        wk = f['conv_w'][layer].float()              # (kh,kw,out,in), bf16-rounded
+        ref = torch.nn.functional.conv2d(x.to(torch.bfloat16).float().permute(0, 3, 1, 2),
+                                         wk.permute(2, 3, 0, 1).contiguous(), f['conv_b'][layer], padding=1)
+        if use_skip:
+            ref = ref + skip.to(torch.bfloat16).float().permute(0, 3, 1, 2)
+        ref = torch.relu(ref).permute(0, 2, 3, 1)
+        err = (got - ref).abs()
+        tol = 0.02 + 0.01 * ref.abs()                # bf16 output rounding (2^-8 relative) + accumulation order
+        assert bool((err <= tol).all()), "layer %d: max err %g at %s" % (layer, err.max(), np.unravel_index(int(err.argmax()), err.shape))
+        # pad rows must stay zero
+        assert float(out.cpu()[0].abs().max()) == 0 and float(out.cpu()[1:].view(n, W + 1, W, 256)[:, W].abs().max()) == 0
+    e.close()
+
+
+@pytest.mark.parametrize("size,n_blocks,n", [(19, 2, 24), (9, 3, 40), (19, 20, 12)])
+def test_forward_vs_fp32_reference(size, n_blocks, n):
+    from sejonggo_b200 import model
+    params = model.init_params(size, n_blocks, seed=0, randomize_bn=(n_blocks != 20), random_bias=(n_blocks != 20))
+    m = model.TowerModel("t", params=params, max_positions=32)
+    boards = _positions(size, n, seed=size + n_blocks)
+    pol, val = m.predict_on_batch(boards)
+    m.check(m._host_engine, 0)
+    rp, rv = tower_ref.forward(params, boards.astype(np.float32), device="cuda")
+    rp, rv = rp.cpu().numpy(), rv.cpu().numpy()
+    assert pol.shape == (n, size * size + 1) and val.shape == (n, 1)
+    assert np.abs(pol.sum(axis=1) - 1).max() < 1e-4
+    assert np.abs(pol - rp).max() <= TOL, np.abs(pol - rp).max()
+    assert np.abs(val - rv).max() <= TOL, np.abs(val - rv).max()
+
+
+def test_forward_symmetry_fusion():
+    """random_symmetry_predict semantics (symmetry.py:127-132): board gather fused into the stem,
+    the 'reverse' policy gather (same map, Q8) fused into the heads."""
+    from sejonggo_b200 import model
+    from sejonggo_b200.engine import Engine
+    S, n = 9, 16
+    params = model.init_params(S, 2, seed=5, randomize_bn=True, random_bias=True)
+    m = model.TowerModel("t", params=params, max_positions=32)
+    boards = _positions(S, n, seed=77)
+    e = Engine(size=S, n_games=n, max_leaves=1, arena_blocks=2)
+    e.import_boards(boards)
+    idx = torch.arange(n, device=e.device)
+    syms = torch.as_tensor(np.arange(n) % 8, dtype=torch.int32, device=e.device)
+    pol, val = m.evaluate(e, 0, idx, syms, slot=0)
+    m.check(e, 0)
+    pol, val = pol.cpu().numpy(), val.cpu().numpy()
+    for i in range(n):
+        k = int(syms[i])
+        sb = o.sym_board(k, boards[i:i + 1])
+        rp, rv = tower_ref.forward(params, sb.astype(np.float32), device="cuda")
+        rp = o.sym_policy(k, rp.cpu().numpy(), S)
+        assert np.abs(pol[i] - rp[0]).max() <= TOL and abs(val[i] - float(rv[0, 0])) <= TOL, (i, k)
+    # gather by index / chunking over max_positions
+    perm = torch.as_tensor(np.random.RandomState(0).permutation(n), device=e.device)
+    m2 = model.TowerModel("t2", params=params, max_positions=5)
+    p2, v2 = m2.evaluate(e, 0, perm, syms[perm], slot=1)
+    assert np.abs(p2.cpu().numpy() - pol[perm.cpu().numpy()]).max() < 1e-6
+    e.close()
+
+
+def test_self_play_with_tower_runs():
+    """End-to-end: play_games with the CUDA tower as the evaluator (mode A and mode B)."""
+    from sejonggo_b200 import model, self_play as sp, nomodel_self_play as nsp, predicting_queue_worker as pq
+    from sejonggo_b200.conf import conf
+    old = dict(conf)
+    try:
+        conf.update(SIZE=9, MCTS_BATCH_SIZE=8, ENERGY=8, MCTS_SIMULATIONS=16, KOMI=5.5)
+        m = model.TowerModel("model_1", size=9, n_blocks=2, seed=1, max_positions=256)
+        games = sp.play_games(m, m, 6, 16, 3, self_play=True, num_moves=6)
+        assert len(games) == 6 and all(len(g['moves']) == 6 for g in games)
+        assert all(abs(mv['policy'].sum() - 1.0) < 0.3 for g in games for mv in g['moves'][1:])
+        pq.register_models(best=m, latest=m)
+        games = nsp.play_games_async("BEST_SYM", "BEST_SYM", 4, 8, 3, self_play=True, num_moves=5, exact_rng_order=False)
+        assert len(games) == 4 and all(len(g['moves']) == 5 for g in games)
+    finally:
+        conf.clear()
+        conf.update(old)
