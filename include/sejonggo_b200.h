@@ -113,6 +113,8 @@ int sgo_tree_download_sync(sgo_engine *e, int32_t tree, void *h_blocks, int32_t 
 int sgo_tree_upload_sync(sgo_engine *e, int32_t tree, const void *h_blocks, int32_t n_blocks, const void *h_meta, const double *h_root_p64);
 /* leaf bookkeeping: int32 [G] leaves selected in the last select call */
 int sgo_leaf_counts(sgo_engine *e, int32_t *d_counts, void *stream);
+/* device list of leaf slots awaiting evaluation (unordered); h_count = how many (synchronises) */
+int sgo_leaf_compact_sync(sgo_engine *e, int32_t *d_index, int32_t *h_count, void *stream);
 int sgo_tree_valid(sgo_engine *e, const int32_t *d_tree_sel, int32_t *d_valid, void *stream);
 
 /* ---- network: model.py:37-96 (Keras/TF1.7 residual tower; the arithmetic lives in that

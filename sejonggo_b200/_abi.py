@@ -53,6 +53,7 @@ _PROTOS = {
     "sgo_tree_upload_sync": [vp, i32, vp, i32, vp, vp],
     "sgo_leaf_counts": [vp, vp, vp],
     "sgo_tree_valid": [vp, vp, vp, vp],
+    "sgo_leaf_compact_sync": [vp, vp, C.POINTER(i32), vp],
     "sgo_tower_load_weights": [vp, i32, vp, i32, vp],
     "sgo_tower_free": [vp, i32],
     "sgo_tower_forward": [vp, i32, i32, vp, i32, vp, i32, vp, vp, vp],

@@ -109,6 +109,8 @@ class BatchedGames(object):
         self.eng = engine or Engine(size=size, n_games=n_games, trees_per_game=T, max_leaves=self.batch,
                                     arena_blocks=arena_blocks, komi=komi, device=device)
         self.resign = [self._per_game(resign[0]), self._per_game(resign[1])]
+        # device fast path: every evaluator is a GPU tower and draws are not injected per game
+        self.fast = all(hasattr(ev, "is_sgo_evaluator") for ev in self.ev) and rngs is None
         self.sim_count = 0            # leaves expanded + backed up (the north-star "simulations")
         self.eval_count = 0
         self.plies_done = 0
@@ -217,6 +219,64 @@ class BatchedGames(object):
                     break
             e.backup_b(self.energy, tree_sel)
 
+    # ------------------------------------------------- device-resident search (TowerModel evaluators)
+    def _eval_leaves_device(self, tree_sel_dev, cur_model_dev, syms_game):
+        """Evaluate every leaf slot awaiting evaluation; returns dense per-slot buffers."""
+        e = self.eng
+        if getattr(self, "_pbuf", None) is None:
+            self._pbuf = torch.zeros((e.G * e.L, e.A), dtype=torch.float32, device=e.device)
+            self._vbuf = torch.zeros((e.G * e.L,), dtype=torch.float32, device=e.device)
+        idx, n = e.leaf_compact()
+        if n == 0:
+            return 0
+        games = torch.div(idx, e.L, rounding_mode='floor').long()
+        syms = None if syms_game is None else syms_game[games].contiguous()
+        groups = [(0, idx, syms)]
+        if not self.same_model:
+            mm = cur_model_dev[games]
+            groups = [(mi, idx[mm == mi].contiguous(), None if syms is None else syms[mm == mi].contiguous()) for mi in (0, 1)]
+        for mi, ix, sy in groups:
+            if ix.numel() == 0:
+                continue
+            p, v = self.ev[mi].evaluate(e, 1, ix, sy, slot=mi)
+            self._pbuf[ix.long()] = p
+            self._vbuf[ix.long()] = v
+        self.eval_count += n
+        return n
+
+    def _draw_syms_device(self):
+        if not self.use_symmetry:
+            return None
+        r = self.rngs[0]
+        seed = int(r.r.randint(1 << 31)) if hasattr(r, "r") else 0
+        g = torch.Generator(device=self.eng.device).manual_seed(seed)
+        return torch.randint(0, 7, (self.G,), generator=g, device=self.eng.device, dtype=torch.int32)
+
+    def _search_a_device(self, tree_sel_dev, cur_model_dev):
+        e = self.eng
+        for _ in range(int(self.sims / self.batch)):
+            e.select_a(self.batch, tree_sel_dev)
+            n = self._eval_leaves_device(tree_sel_dev, cur_model_dev, self._draw_syms_device())
+            e.expand(self._pbuf, self._vbuf, tree_sel_dev)
+            e.backup_a(tree_sel_dev)
+            self.sim_count += n
+
+    def _search_b_device(self, tree_sel_dev, cur_model_dev):
+        e = self.eng
+        for _ in range(int(self.sims / self.energy)):
+            restart = True
+            while True:
+                newly, stalled = e.select_b(self.batch, restart, tree_sel_dev)
+                restart = False
+                if newly == 0:
+                    break
+                n = self._eval_leaves_device(tree_sel_dev, cur_model_dev, self._draw_syms_device())
+                e.expand(self._pbuf, self._vbuf, tree_sel_dev)
+                self.sim_count += n
+                if stalled == 0:
+                    break
+            e.backup_b(self.energy, tree_sel_dev)
+
     # ------------------------------------------------------------------ run
     def run(self, exact_rng_order=True):
         e, G, S, A = self.eng, self.G, self.S, self.A
@@ -268,7 +328,14 @@ class BatchedGames(object):
                         noise[g] = self.rngs[g].dirichlet(A)
                 e.tree_new(policy, noise=noise, eps=self.eps, force=False, tree_sel=np.where(need, tree_sel, -1).astype(np.int32))
             # search
-            if self.mode == 'a':
+            if self.fast:
+                ts_dev = e.dev(tree_sel, torch.int32)
+                cm_dev = e.dev(cur_model, torch.int64)
+                if self.mode == 'a':
+                    self._search_a_device(ts_dev, cm_dev)
+                else:
+                    self._search_b_device(ts_dev, cm_dev)
+            elif self.mode == 'a':
                 self._search_a(tree_sel, active, cur_model)
             elif exact_rng_order:
                 self._search_b(tree_sel, active, cur_model)
@@ -278,7 +345,10 @@ class BatchedGames(object):
             prior, count, _ = e.child_stats(tree_sel, want=("prior", "count"))
             prior_h = prior.cpu().numpy()
             forced = None
-            if temperature == 1:
+            u01 = None
+            if temperature == 1 and self.fast:
+                u01 = np.array([self.rngs[0].uniform() for _ in range(G)], np.float64)    # device-side sampling
+            elif temperature == 1:
                 count_h = count.cpu().numpy()
                 forced = np.full(G, -1, np.int32)
                 for g in act_idx:
@@ -286,7 +356,7 @@ class BatchedGames(object):
                     total = int(count_h[g].sum())
                     forced[g] = self.rngs[g].choice([int(m) for m in nz], [int(count_h[g][m]) / float(total) for m in nz])
             temps = np.full(G, temperature, np.int32)
-            index = e.pick(temps, None, forced, tree_sel).cpu().numpy()
+            index = e.pick(temps, u01, forced, tree_sel).cpu().numpy()
             if self.record_boards == 'full':
                 boards_h = e.export_boards().cpu().numpy()
             elif self.record_boards == 'packed':

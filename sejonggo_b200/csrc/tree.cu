@@ -583,6 +583,20 @@ __global__ void k_tree_valid(int G, int T, const TreeMeta *meta, const int32_t *
     valid[g] = ts < 0 ? 0 : meta[g * T + ts].valid;
 }
 
+
+// indices of leaf slots awaiting evaluation (state == 1), warp-aggregated append
+__global__ void k_leaf_compact(const LeafRef *leaf_refs, int total, int32_t *index, int32_t *count)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x, lane = lane_id();
+    bool v = i < total && leaf_refs[i].state == 1;
+    unsigned bal = __ballot_sync(SGO_FULL, v);
+    if (!bal) return;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(count, __popc(bal));
+    base = __shfl_sync(SGO_FULL, base, 0);
+    if (v) index[base + __popc(bal & ((1u << lane) - 1u))] = i;
+}
+
 // ------------------------------------------------------------------ C ABI
 #define LAUNCH_OK(e) SGO_CUDA_OK(e, cudaGetLastError())
 
@@ -685,6 +699,19 @@ extern "C" int sgo_tree_valid(sgo_engine *e, const int32_t *d_tree_sel, int32_t 
 extern "C" int sgo_leaf_counts(sgo_engine *e, int32_t *d_counts, void *stream)
 {
     SGO_CUDA_OK(e, cudaMemcpyAsync(d_counts, e->leaf_count, sizeof(int32_t) * e->G, cudaMemcpyDeviceToDevice, S_(stream)));
+    return 0;
+}
+
+
+extern "C" int sgo_leaf_compact_sync(sgo_engine *e, int32_t *d_index, int32_t *h_count, void *stream)
+{
+    int total = e->G * e->L;
+    SGO_CUDA_OK(e, cudaMemsetAsync(e->counters + 2, 0, sizeof(int32_t), S_(stream)));
+    k_leaf_compact<<<(total + 255) / 256, 256, 0, S_(stream)>>>(e->leaf_refs, total, d_index, e->counters + 2);
+    LAUNCH_OK(e);
+    SGO_CUDA_OK(e, cudaMemcpyAsync(e->h_pinned + 7, e->counters + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, S_(stream)));
+    SGO_CUDA_OK(e, cudaStreamSynchronize(S_(stream)));
+    if (h_count) *h_count = e->h_pinned[7];
     return 0;
 }
 

@@ -205,6 +205,14 @@ class Engine(object):
         self._ck(self.lib.sgo_leaf_counts(self.h, self._p(out), self._stream()))
         return out
 
+    def leaf_compact(self):
+        """-> (int32 device tensor of leaf slots awaiting evaluation, count)"""
+        if getattr(self, "_compact_buf", None) is None:
+            self._compact_buf = torch.empty((self.G * self.L,), dtype=torch.int32, device=self.device)
+        n = C.c_int32(0)
+        self._ck(self.lib.sgo_leaf_compact_sync(self.h, self._p(self._compact_buf), C.byref(n), self._stream()))
+        return self._compact_buf[:n.value], n.value
+
     def tree_valid(self, tree_sel=None):
         ts = self.dev(tree_sel, torch.int32)
         out = torch.empty((self.G,), dtype=torch.int32, device=self.device)
