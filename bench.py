@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""bench.py — self-play MCTS throughput on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode a|b]
+
+A "step" is one ply of EVERY concurrent game: root evaluation, new trees where needed,
+MCTS_SIMULATIONS simulations (mode A: sims/100 batched top-N steps, self_play.py:28-152;
+mode B: sims/8 virtual-loss waves, nomodel_self_play.py:59-140), move pick, re-root and
+make_play.  Workload = BASELINE.json configs[2]: 19x19, conf.py default tower (20 blocks x
+256 ch, random init), 800 sims/ply, 1024 concurrent games per GPU (weak scaling: configs[4]
+is 8 x 1024).  `value` = simulations (leaves expanded + backed up) per second summed over
+GPUs with every input resident in HBM; `e2e` = the same through the public batched API with
+the per-ply records (packed board, policy target, value, move) copied to host memory and the
+host-drawn noise / sampling inputs copied to the device inside the timed region.
+
+--impl reference times the reference's CPU path: /root/reference is pure Python and absent on
+the GPU box, so this runs the pinned C oracle port (oracle/go_oracle.c, kind "port") of the
+same self-play loop with a free uniform evaluator on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SIZE, SIMS, BATCH_A, ENERGY_B, BLOCKS, GAMES_PER_GPU = 19, 800, 100, 8, 20, 1024
+FLOP_PER_CONV_POS = 2.0 * 17 * 17 * 256 * 256 * 9           # one 3x3 256->256 layer, one position
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(tflops=float(p["bf16_tflops_sustained"]), hbm=float(p["hbm_gbs"]), src="measured (sustained)")
+    except Exception:
+        return dict(tflops=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu=0):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace('.', '').isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, nm in enumerate(names):
+                if len(r) > 5 + i and r[5 + i].lower().startswith("active"):
+                    reasons.add(nm)
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------ CPU arm
+class _Uniform(object):
+    """Free evaluator: policy 1/(S*S+1), value 0 — the CPU number excludes network cost."""
+    name = "uniform"
+
+    def predict_on_batch(self, X):
+        import numpy as np
+        X = np.asarray(X)
+        n, S = X.shape[0], X.shape[1]
+        return np.full((n, S * S + 1), 1.0 / (S * S + 1), np.float32), np.zeros((n, 1), np.float32)
+
+
+def _cpu_worker(args):
+    seed, mode, plies = args
+    from oracle import game_loop as gl
+    m = _Uniform()
+    t0 = time.time()
+    if mode == 'a':
+        gd = gl.play_game(m, m, SIMS, 30, self_play=True, num_moves=plies, size=SIZE, mcts_batch_size=BATCH_A, rng=gl.SeededRng(seed))
+    else:
+        gd = gl.play_game_async("BEST_SYM", "BEST_SYM", ENERGY_B, 30, 0, self_play=True, num_moves=plies, size=SIZE,
+                                conf_sims=SIMS, conf_energy=ENERGY_B, rng=gl.SeededRng(seed),
+                                predict=lambda tag, b, sym: (lambda p, v: (p[0], v[0]))(*gl.sym_predict(m, b, sym)))
+    return len(gd['moves']), time.time() - t0
+
+
+def cpu_selfplay(mode, plies_per_game, rounds=1):
+    """All host cores, one game per process (the reference's own parallelism, main_selfplay.py:26)."""
+    import multiprocessing as mp
+    from oracle import oracle as o
+    o.build()
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    t0 = time.time()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(1000 + i, mode, plies_per_game) for i in range(cores * rounds)])
+    wall = time.time() - t0
+    plies = sum(r[0] for r in res)
+    per = SIMS // (BATCH_A if mode == 'a' else ENERGY_B) * (BATCH_A if mode == 'a' else ENERGY_B)
+    return dict(sims=plies * per, plies=plies, wall=wall, cores=cores)
+
+
+CPU_PLIES_PER_STEP = 10      # one CPU "step" = 10 plies of one game on every host core (~2 s of work per core)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(1, a.steps), a.warmup
+    cpu_selfplay(a.mode, max(1, min(warm, 3)))                  # untimed warm-up (builds/loads the oracle, forks once)
+    plies = CPU_PLIES_PER_STEP * steps
+    r = cpu_selfplay(a.mode, plies)
+    val = r['sims'] / r['wall']
+    cb = dict(value=val, unit="simulations/s", cores=r['cores'], kind="port",
+              sample="%d games (one per core) x %d plies, 19x19, %d sims/ply, mode %s, uniform evaluator (network cost excluded); "
+                     "C oracle port of the pure-Python reference, which itself measured 179 sims/s/core in the survey container"
+                     % (r['cores'], plies, SIMS, a.mode.upper()))
+    print(json.dumps(dict(
+        impl="reference", metric="selfplay_mcts_simulations_per_sec", value=val, unit="simulations/s", n_gpus=a.gpus,
+        steps=steps, warmup=warm, ms_per_step=1e3 * r['wall'] / steps, higher_is_better=True, scaling="weak",
+        vs_baseline=None, dtype="f32", data="synthetic",
+        config=dict(workload="19x19 self-play, %d sims/ply, mode %s, one game per host core" % (SIMS, a.mode.upper()),
+                    moves_per_sec=r['plies'] / r['wall'], step="%d plies of one game per core" % CPU_PLIES_PER_STEP),
+        cpu_baseline=cb, e2e=dict(value=val, unit="simulations/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_ours(a):
+    import numpy as np
+    import torch
+    from sejonggo_b200 import dist as sd, model
+    from sejonggo_b200.batched import BatchedGames, HostRng
+    rank, world, local = sd.init()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    G = a.games
+    batch = BATCH_A if a.mode == 'a' else ENERGY_B
+    params = model.init_params(SIZE, a.blocks, seed=0 if rank == 0 else 1 + rank)
+    if world > 1:
+        sd.broadcast_params(params, src=0, device=dev)           # NCCL weight broadcast
+    m = model.TowerModel("model_1", params=params, max_positions=a.max_positions)
+    arena = a.arena or 4 * (SIMS + batch)
+    bg = BatchedGames((m, m), G, size=SIZE, mode=a.mode, mcts_batch_size=BATCH_A, energy=ENERGY_B, mcts_simulations=a.sims,
+                      stop_exploration=30, self_play=True, rng=HostRng(1234 + rank), arena_blocks=arena, device=local,
+                      record_boards='packed')
+    e = bg.eng
+    m.attach(e, 0)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            torch.distributed.barrier()
+
+    def timed(n_steps, record):
+        sync_all()
+        s0, p0, l0 = bg.sim_count, bg.plies_done, e.launch_count()
+        h0, d0 = bg.h2d_bytes, bg.d2h_bytes
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(n_steps):
+            bg.step_ply(record=record)
+        ev1.record()
+        sync_all()
+        ms = ev0.elapsed_time(ev1)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        cnt = torch.tensor([bg.sim_count - s0, bg.plies_done - p0], dtype=torch.float64, device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)      # max over ranks, device timed
+            torch.distributed.all_reduce(cnt, op=torch.distributed.ReduceOp.SUM)
+        return dict(ms=float(t.item()), sims=float(cnt[0].item()), plies=float(cnt[1].item()), launches=e.launch_count() - l0,
+                    h2d=bg.h2d_bytes - h0, d2h=bg.d2h_bytes - d0)
+
+    bg.start()
+    for _ in range(a.warmup):
+        bg.step_ply(record=False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    m.profile(e, 0, True)
+    r = timed(a.steps, record=False)
+    prof = m.profile_read(e, 0)
+    m.profile(e, 0, False)
+    clocks = sampler.stop() if rank == 0 else None
+    r2 = timed(a.steps, record=True)                               # end-to-end through the public batched API
+    e.check_errors()
+    m.check(e, 0)
+    records = sd.pack_records(bg.finish())
+    gathered = sd.gather_records(records.to(dev) if world > 1 else records, dst=0, device=dev if world > 1 else None)
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    conv_flops = prof['positions'] * FLOP_PER_CONV_POS * 2 * a.blocks
+    conv_s = prof['conv_ms'] * 1e-3
+    achieved = conv_flops / conv_s / 1e12 if conv_s > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "conv_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    out = dict(
+        metric="selfplay_mcts_simulations_per_sec", value=r['sims'] / (r['ms'] * 1e-3), unit="simulations/s", n_gpus=world,
+        steps=a.steps, warmup=a.warmup, ms_per_step=r['ms'] / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+        dtype="bf16", data="synthetic",
+        config=dict(workload="19x19 self-play, conf.py default tower (%d blocks x 256 ch, random init), %d sims/ply, %d concurrent "
+                             "games per GPU, mode %s" % (a.blocks, a.sims, G, a.mode.upper()),
+                    games_per_gpu=G, mode=a.mode, sims_per_ply=a.sims, moves_per_sec=r['plies'] / (r['ms'] * 1e-3),
+                    l2="working set (trees %.1f GB, activations %.1f GB) >> 126 MB L2; no flush needed" %
+                       (G * 2 * arena * 6272 / 1e9, 3 * (a.max_positions * 18 + 1) * 17 * 512 / 1e9),
+                    step="one ply of every game", parallelism="games sharded, %d rank(s)" % world,
+                    records_gathered=None if gathered is None else [int(g.numel()) for g in gathered]),
+        e2e=dict(value=r2['sims'] / (r2['ms'] * 1e-3), unit="simulations/s", h2d_bytes_per_step=r2['h2d'] / a.steps,
+                 d2h_bytes_per_step=r2['d2h'] / a.steps, moves_per_sec=r2['plies'] / (r2['ms'] * 1e-3)),
+        gpu_launches=r['launches'],
+        clocks=clocks,
+        roofline=dict(bound="tensor", kernel="k_conv3x3_tc", achieved=achieved, peak=peaks['tflops'], unit="TFLOP/s",
+                      frac=achieved / peaks['tflops'], traffic=traffic, peak_source=peaks['src'],
+                      launches=prof['conv_launches'], avg_launch_ms=prof['conv_ms'] / max(1, prof['conv_launches']),
+                      share_of_step=prof['conv_ms'] / r['ms'], stem_ms=prof['stem_ms'], heads_ms=prof['heads_ms']),
+    )
+    if world == 1 and not a.no_cpu:
+        cpu_selfplay(a.mode, 1)
+        c = cpu_selfplay(a.mode, 20)
+        out["cpu_baseline"] = dict(
+            value=c['sims'] / c['wall'], unit="simulations/s", cores=c['cores'], kind="port",
+            sample="%d games (one per core) x 20 plies, 19x19, %d sims/ply, mode %s, uniform evaluator (network cost excluded), C oracle port"
+                   % (c['cores'], SIMS, a.mode.upper()))
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="a", choices=["a", "b"])
+    ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
+    ap.add_argument("--sims", type=int, default=SIMS)
+    ap.add_argument("--blocks", type=int, default=BLOCKS)
+    ap.add_argument("--max-positions", type=int, default=16384)
+    ap.add_argument("--arena", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

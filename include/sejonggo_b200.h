@@ -47,6 +47,8 @@ const char *sgo_last_error(sgo_engine *e);
 /* reads and clears the sticky device error flags (synchronises `stream`) */
 int sgo_check_errors_sync(sgo_engine *e, void *stream, int32_t *h_flags);
 int sgo_abi_version(void);
+/* number of kernels this engine has launched so far (bench.py's gpu_launches) */
+int64_t sgo_launch_count(sgo_engine *e);
 
 /* ---- rules engine: play.py ------------------------------------------------ */
 /* play.py:295-299 game_init for games [first, first+n) */
@@ -151,6 +153,10 @@ int sgo_tower_forward(sgo_engine *e, int32_t slot, int32_t which, const int32_t 
                       const int32_t *d_sym, int32_t scatter, float *d_policy, float *d_value, void *stream);
 /* sticky tower error flags (16 = an mbarrier wait timed out); synchronises */
 int sgo_tower_check_sync(sgo_engine *e, int32_t slot, int32_t *h_flags, void *stream);
+/* live CUDA-event timing of the tower kernels on the launching stream (bench.py roofline):
+ * h_out[6] = ms in stem, ms in conv layers, ms in heads, conv launches, positions, forward calls */
+int sgo_tower_profile(sgo_engine *e, int32_t slot, int32_t enable);
+int sgo_tower_profile_read_sync(sgo_engine *e, int32_t slot, double *h_out);
 /* test / profiling hooks: one tensor-core conv layer in isolation; raw activation buffers
  * bf16 [n*(S-1)+1][S-2][C] (row 0 and every (S-1)-th row are zero padding) */
 int sgo_tower_debug_conv(sgo_engine *e, int32_t slot, int32_t n, int32_t layer, int32_t in, int32_t out, int32_t skip, void *stream);

@@ -58,6 +58,8 @@ _PROTOS = {
     "sgo_tower_free": [vp, i32],
     "sgo_tower_forward": [vp, i32, i32, vp, i32, vp, i32, vp, vp, vp],
     "sgo_tower_check_sync": [vp, i32, C.POINTER(i32), vp],
+    "sgo_tower_profile": [vp, i32, i32],
+    "sgo_tower_profile_read_sync": [vp, i32, vp],
     "sgo_tower_debug_conv": [vp, i32, i32, i32, i32, i32, i32, vp],
     "sgo_tower_act_copy": [vp, i32, i32, i32, vp, i32, vp],
 }
@@ -87,6 +89,8 @@ def load(build_if_needed=True):
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = C.c_int
+    lib.sgo_launch_count.argtypes = [vp]
+    lib.sgo_launch_count.restype = C.c_int64
     lib.sgo_last_error.argtypes = [vp]
     lib.sgo_last_error.restype = C.c_char_p
     _lib = lib

@@ -279,113 +279,146 @@ class BatchedGames(object):
 
     # ------------------------------------------------------------------ run
     def run(self, exact_rng_order=True):
-        e, G, S, A = self.eng, self.G, self.S, self.A
+        self.start()
+        for _ in range(self.num_moves):
+            if not self.step_ply(exact_rng_order=exact_rng_order):
+                break
+        return self.finish()
+
+    def start(self):
+        e, G = self.eng, self.G
         e.reset()
         e.tree_reset()
         # choose_first_player (play.py:301-306): cur_model[g] in {0,1} indexes (model1, model2)
-        cur_model = np.array([0 if self.rngs[g].coin() < .5 else 1 for g in range(G)], np.int32)
-        model1_isblack = cur_model == 0
-        # tree index per game: in self-play one shared tree (Q16); else model k searches tree k
-        active = np.ones(G, bool)
-        skipped_last = np.zeros(G, bool)
-        end_reason = np.array(["PLAYED ALL MOVES"] * G, dtype=object)
-        player = np.ones(G, np.int32)               # move_data['player'] (lags one ply, self_play.py:236)
-        moves_rec = [[] for _ in range(G)]
-        temperature = 1
-        for move_n in range(self.num_moves):
-            if not active.any():
-                break
-            if move_n == self.stop_exploration:
-                temperature = 0
-            tree_sel = np.where(active, 0 if self.self_play else cur_model, -1).astype(np.int32)
-            act_idx = np.nonzero(active)[0].astype(np.int64)
-            # root evaluation (self_play.py:187 / nomodel_self_play.py:165)
-            rsyms = None
-            if self.root_symmetry and self.use_symmetry:
-                rsyms = np.zeros(G, np.int32)
-                for g in act_idx:
-                    rsyms[g] = self.rngs[g].symmetry()
-            policy, value = self._evaluate(0, act_idx, cur_model, rsyms)
-            value_h = value.cpu().numpy()
-            # resignation (self_play.py:190-193)
-            thr = np.where(cur_model == 0, self.resign[0], self.resign[1])
-            with np.errstate(invalid='ignore'):
-                resigning = active & ~np.isnan(thr) & (thr != 0) & (value_h <= thr)
-            for g in np.nonzero(resigning)[0]:
-                end_reason[g] = "resign"
-            active = active & ~resigning
-            if not active.any():
-                break
-            tree_sel = np.where(active, 0 if self.self_play else cur_model, -1).astype(np.int32)
-            # new trees only where there is no reusable subtree (self_play.py:195-198)
-            valid = e.tree_valid(tree_sel).cpu().numpy()
-            need = active & (valid == 0)
-            if need.any():
-                noise = None
-                if self.self_play:
-                    noise = np.zeros((G, A), np.float64)
-                    for g in np.nonzero(need)[0]:
-                        noise[g] = self.rngs[g].dirichlet(A)
-                e.tree_new(policy, noise=noise, eps=self.eps, force=False, tree_sel=np.where(need, tree_sel, -1).astype(np.int32))
-            # search
-            if self.fast:
-                ts_dev = e.dev(tree_sel, torch.int32)
-                cm_dev = e.dev(cur_model, torch.int64)
-                if self.mode == 'a':
-                    self._search_a_device(ts_dev, cm_dev)
-                else:
-                    self._search_b_device(ts_dev, cm_dev)
-            elif self.mode == 'a':
-                self._search_a(tree_sel, active, cur_model)
-            elif exact_rng_order:
-                self._search_b(tree_sel, active, cur_model)
-            else:
-                self._search_b_fast(tree_sel, active, cur_model)
-            # move pick (self_play.py:138-152)
-            prior, count, _ = e.child_stats(tree_sel, want=("prior", "count"))
-            prior_h = prior.cpu().numpy()
-            forced = None
-            u01 = None
-            if temperature == 1 and self.fast:
-                u01 = np.array([self.rngs[0].uniform() for _ in range(G)], np.float64)    # device-side sampling
-            elif temperature == 1:
-                count_h = count.cpu().numpy()
-                forced = np.full(G, -1, np.int32)
-                for g in act_idx:
-                    nz = np.nonzero(count_h[g])[0]
-                    total = int(count_h[g].sum())
-                    forced[g] = self.rngs[g].choice([int(m) for m in nz], [int(count_h[g][m]) / float(total) for m in nz])
-            temps = np.full(G, temperature, np.int32)
-            index = e.pick(temps, u01, forced, tree_sel).cpu().numpy()
-            if self.record_boards == 'full':
-                boards_h = e.export_boards().cpu().numpy()
-            elif self.record_boards == 'packed':
-                boards_h = e.export_packed(0).cpu().numpy().view(np.uint32)
-            else:
-                boards_h = None
-            apply = np.full(G, -1, np.int32)
+        self.cur_model = np.array([0 if self.rngs[g].coin() < .5 else 1 for g in range(G)], np.int32)
+        self.model1_isblack = self.cur_model == 0
+        self.active = np.ones(G, bool)
+        self.skipped_last = np.zeros(G, bool)
+        self.end_reason = np.array(["PLAYED ALL MOVES"] * G, dtype=object)
+        self.player = np.ones(G, np.int32)          # move_data['player'] (lags one ply, self_play.py:236)
+        self.moves_rec = [[] for _ in range(G)]
+        self.temperature = 1
+        self.move_n = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def step_ply(self, exact_rng_order=True, record=True):
+        """One ply of every active game.  Returns False when no game is left."""
+        e, G, S, A = self.eng, self.G, self.S, self.A
+        active, cur_model, move_n = self.active, self.cur_model, self.move_n
+        if not active.any() or move_n >= self.num_moves:
+            return False
+        if move_n == self.stop_exploration:
+            self.temperature = 0
+        temperature = self.temperature
+        tree_sel = np.where(active, 0 if self.self_play else cur_model, -1).astype(np.int32)
+        act_idx = np.nonzero(active)[0].astype(np.int64)
+        # root evaluation (self_play.py:187 / nomodel_self_play.py:165)
+        rsyms = None
+        if self.root_symmetry and self.use_symmetry:
+            rsyms = np.zeros(G, np.int32)
             for g in act_idx:
-                idx = int(index[g])
-                x, y = idx % S, idx // S
-                moves_rec[g].append(dict(
+                rsyms[g] = self.rngs[g].symmetry()
+        policy, value = self._evaluate(0, act_idx, cur_model, rsyms)
+        value_h = value.cpu().numpy()
+        self.d2h_bytes += value_h.nbytes
+        # resignation (self_play.py:190-193)
+        thr = np.where(cur_model == 0, self.resign[0], self.resign[1])
+        with np.errstate(invalid='ignore'):
+            resigning = active & ~np.isnan(thr) & (thr != 0) & (value_h <= thr)
+        for g in np.nonzero(resigning)[0]:
+            self.end_reason[g] = "resign"
+        active &= ~resigning
+        if not active.any():
+            return False
+        tree_sel = np.where(active, 0 if self.self_play else cur_model, -1).astype(np.int32)
+        act_idx = np.nonzero(active)[0].astype(np.int64)
+        # new trees only where there is no reusable subtree (self_play.py:195-198)
+        valid = e.tree_valid(tree_sel).cpu().numpy()
+        need = active & (valid == 0)
+        if need.any():
+            noise = None
+            if self.self_play:
+                noise = np.zeros((G, A), np.float64)
+                for g in np.nonzero(need)[0]:
+                    noise[g] = self.rngs[g].dirichlet(A)
+                self.h2d_bytes += noise.nbytes
+            e.tree_new(policy, noise=noise, eps=self.eps, force=False, tree_sel=np.where(need, tree_sel, -1).astype(np.int32))
+        # search
+        if self.fast:
+            ts_dev = e.dev(tree_sel, torch.int32)
+            cm_dev = e.dev(cur_model, torch.int64)
+            self.h2d_bytes += tree_sel.nbytes + cur_model.nbytes
+            if self.mode == 'a':
+                self._search_a_device(ts_dev, cm_dev)
+            else:
+                self._search_b_device(ts_dev, cm_dev)
+        elif self.mode == 'a':
+            self._search_a(tree_sel, active, cur_model)
+        elif exact_rng_order:
+            self._search_b(tree_sel, active, cur_model)
+        else:
+            self._search_b_fast(tree_sel, active, cur_model)
+        # move pick (self_play.py:138-152)
+        forced = None
+        u01 = None
+        prior_h = None
+        if record:
+            prior, count, _ = e.child_stats(tree_sel, want=("prior", "count"))
+            prior_h = prior.cpu().numpy()                       # policy_target = root priors (Q14)
+            self.d2h_bytes += prior_h.nbytes
+        if temperature == 1 and self.fast:
+            u01 = np.array([self.rngs[0].uniform() for _ in range(G)], np.float64)    # device-side sampling
+            self.h2d_bytes += u01.nbytes
+        elif temperature == 1:
+            if not record:
+                _, count, _ = e.child_stats(tree_sel, want=("count",))
+            count_h = count.cpu().numpy()
+            forced = np.full(G, -1, np.int32)
+            for g in act_idx:
+                nz = np.nonzero(count_h[g])[0]
+                total = int(count_h[g].sum())
+                forced[g] = self.rngs[g].choice([int(m) for m in nz], [int(count_h[g][m]) / float(total) for m in nz])
+        temps = np.full(G, temperature, np.int32)
+        index_dev = e.pick(temps, u01, forced, tree_sel)
+        index = index_dev.cpu().numpy()
+        self.d2h_bytes += index.nbytes
+        boards_h = None
+        if record and self.record_boards == 'full':
+            boards_h = e.export_boards().cpu().numpy()
+        elif record and self.record_boards == 'packed':
+            boards_h = e.export_packed(0).cpu().numpy().view(np.uint32)
+        if boards_h is not None:
+            self.d2h_bytes += boards_h.nbytes
+        apply = np.full(G, -1, np.int32)
+        for g in act_idx:
+            idx = int(index[g])
+            x, y = idx % S, idx // S
+            if record:
+                self.moves_rec[g].append(dict(
                     board=None if boards_h is None else (boards_h[g:g + 1].copy() if self.record_boards == 'full' else boards_h[g].copy()),
-                    policy=prior_h[g].copy(), value=value_h[g], move=(x, y), move_n=move_n, player=int(player[g])))
-                if skipped_last[g] and y == S:
-                    end_reason[g] = "BOTH_PASSED"
-                    active[g] = False
-                    continue
-                skipped_last[g] = y == S
-                apply[g] = idx
-            # update trees, play the move, swap sides (self_play.py:223-238)
-            e.reroot(apply)
-            mover = np.where(apply >= 0, self._to_move(), 0)
-            e.apply_moves(apply)
-            moved = apply >= 0
-            player = np.where(moved, mover, player).astype(np.int32)
-            cur_model = np.where(moved, 1 - cur_model, cur_model).astype(np.int32)
-            self.plies_done += int(moved.sum())
-        e.check_errors()
-        return self._finish(model1_isblack, end_reason, player, moves_rec)
+                    policy=prior_h[g].copy(), value=value_h[g], move=(x, y), move_n=move_n, player=int(self.player[g])))
+            if self.skipped_last[g] and y == S:
+                self.end_reason[g] = "BOTH_PASSED"
+                active[g] = False
+                continue
+            self.skipped_last[g] = y == S
+            apply[g] = idx
+        # update trees, play the move, swap sides (self_play.py:223-238)
+        e.reroot(apply)
+        mover = np.where(apply >= 0, 1 if move_n % 2 == 0 else -1, 0)      # black moves on even plies
+        e.apply_moves(apply)
+        self.h2d_bytes += 2 * apply.nbytes
+        moved = apply >= 0
+        self.player = np.where(moved, mover, self.player).astype(np.int32)
+        self.cur_model = np.where(moved, 1 - cur_model, cur_model).astype(np.int32)
+        self.plies_done += int(moved.sum())
+        self.move_n += 1
+        return bool(active.any())
+
+    def finish(self):
+        self.eng.check_errors()
+        return self._finish(self.model1_isblack, self.end_reason, self.player, self.moves_rec)
 
     def _to_move(self):
         # plane 16 of every game (+1 black / -1 white): packed word PW-1

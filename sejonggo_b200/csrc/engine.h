@@ -22,6 +22,7 @@ struct sgo_engine {
     int32_t *counters;            // [4] device scratch counters
     int32_t *h_pinned;            // [8] pinned host mirror
     struct sgo_tower *tower[2];   // network weight slots (tower.cu): 0 = model1/best, 1 = model2/tested
+    unsigned long long launches;  // kernels launched through the ABI (bench.py gpu_launches)
     std::string last_error;
 };
 
@@ -32,6 +33,12 @@ struct sgo_engine {
             (e)->last_error = std::string(#call) + ": " + cudaGetErrorString(_err);       \
             return -2;                                                                    \
         }                                                                                 \
+    } while (0)
+
+#define SGO_LAUNCHED(e)                              \
+    do {                                             \
+        (e)->launches++;                             \
+        SGO_CUDA_OK(e, cudaGetLastError());          \
     } while (0)
 
 static inline int sgo_fail(sgo_engine *e, const char *msg, int code = -1)

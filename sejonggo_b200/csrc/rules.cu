@@ -259,6 +259,8 @@ __global__ void k_random_playouts(Board *boards, int S, int first, int n, uint64
 // ---------------------------------------------------------------- C ABI
 extern "C" int sgo_abi_version(void) { return 1; }
 
+extern "C" int64_t sgo_launch_count(sgo_engine *e) { return e ? (int64_t)e->launches : 0; }
+
 extern "C" const char *sgo_last_error(sgo_engine *e) { return e ? e->last_error.c_str() : "null engine"; }
 
 
@@ -276,6 +278,7 @@ extern "C" int sgo_create(const sgo_config *cfg, sgo_engine **out)
     e->S = cfg->size; e->A = cfg->size * cfg->size + 1; e->G = cfg->n_games; e->T = cfg->trees_per_game;
     e->L = cfg->max_leaves; e->NB = cfg->arena_blocks;
     e->tower[0] = e->tower[1] = nullptr;
+    e->launches = 0;
     *out = e;
     SGO_CUDA_OK(e, cudaSetDevice(cfg->device));
     size_t GL = (size_t)e->G * e->L, GT = (size_t)e->G * e->T;
@@ -336,7 +339,7 @@ extern "C" int sgo_games_reset(sgo_engine *e, int32_t first, int32_t n, void *st
     RANGE_OK(e, first, n, e->G);
     if (n == 0) return 0;
     k_games_reset<<<warp_grid(n), WARPS_PER_BLOCK * 32, 0, S_(stream)>>>(e->boards, first, n);
-    SGO_CUDA_OK(e, cudaGetLastError());
+    SGO_LAUNCHED(e);
     return 0;
 }
 
@@ -345,7 +348,7 @@ extern "C" int sgo_apply_moves(sgo_engine *e, int32_t first, int32_t n, const in
     RANGE_OK(e, first, n, e->G);
     if (n == 0) return 0;
     k_apply_moves<<<warp_grid(n), WARPS_PER_BLOCK * 32, 0, S_(stream)>>>(e->boards, e->S, first, n, d_moves, d_colors, e->err_flags);
-    SGO_CUDA_OK(e, cudaGetLastError());
+    SGO_LAUNCHED(e);
     return 0;
 }
 
@@ -354,7 +357,7 @@ extern "C" int sgo_legal_masks(sgo_engine *e, int32_t first, int32_t n, uint8_t 
     RANGE_OK(e, first, n, e->G);
     if (n == 0) return 0;
     k_legal_masks<<<warp_grid(n), WARPS_PER_BLOCK * 32, 0, S_(stream)>>>(e->boards, e->S, first, n, d_mask);
-    SGO_CUDA_OK(e, cudaGetLastError());
+    SGO_LAUNCHED(e);
     return 0;
 }
 
@@ -363,7 +366,7 @@ extern "C" int sgo_score(sgo_engine *e, int32_t first, int32_t n, int32_t *d_out
     RANGE_OK(e, first, n, e->G);
     if (n == 0) return 0;
     k_score<<<warp_grid(n), WARPS_PER_BLOCK * 32, 0, S_(stream)>>>(e->boards, e->S, e->cfg.komi, first, n, d_out);
-    SGO_CUDA_OK(e, cudaGetLastError());
+    SGO_LAUNCHED(e);
     return 0;
 }
 
@@ -372,7 +375,7 @@ extern "C" int sgo_import_boards(sgo_engine *e, int32_t first, int32_t n, const 
     RANGE_OK(e, first, n, e->G);
     if (n == 0) return 0;
     k_import_boards<<<warp_grid(n), WARPS_PER_BLOCK * 32, 0, S_(stream)>>>(e->boards, e->S, first, n, d_boards);
-    SGO_CUDA_OK(e, cudaGetLastError());
+    SGO_LAUNCHED(e);
     return 0;
 }
 
@@ -381,7 +384,7 @@ extern "C" int sgo_export_boards(sgo_engine *e, int32_t first, int32_t n, int32_
     RANGE_OK(e, first, n, e->G);
     if (n == 0) return 0;
     k_export_boards<<<warp_grid(n), WARPS_PER_BLOCK * 32, 0, S_(stream)>>>(e->boards, e->S, first, n, d_boards);
-    SGO_CUDA_OK(e, cudaGetLastError());
+    SGO_LAUNCHED(e);
     return 0;
 }
 
@@ -390,7 +393,7 @@ extern "C" int sgo_export_packed(sgo_engine *e, int32_t which, int32_t first, in
     RANGE_OK(e, first, n, which ? e->G * e->L : e->G);
     if (n == 0) return 0;
     k_export_packed<<<warp_grid(n), WARPS_PER_BLOCK * 32, 0, S_(stream)>>>(which ? e->leaf_boards : e->boards, e->S, first, n, d_out);
-    SGO_CUDA_OK(e, cudaGetLastError());
+    SGO_LAUNCHED(e);
     return 0;
 }
 
@@ -400,7 +403,7 @@ extern "C" int sgo_export_planes(sgo_engine *e, int32_t which, int32_t first, in
     if (sym < 0 || sym > 7) return sgo_fail(e, "symmetry id out of range");
     if (n == 0) return 0;
     k_export_planes<<<n, 256, 0, S_(stream)>>>(which ? e->leaf_boards : e->boards, e->S, first, n, sym, d_sym, d_out);
-    SGO_CUDA_OK(e, cudaGetLastError());
+    SGO_LAUNCHED(e);
     return 0;
 }
 
@@ -411,7 +414,7 @@ extern "C" int sgo_policy_unsym(sgo_engine *e, int32_t n, int32_t sym, const int
     if (n == 0) return 0;
     int total = n * e->A;
     k_policy_unsym<<<(total + 255) / 256, 256, 0, S_(stream)>>>(e->S, n, sym, d_sym, d_in, d_out);
-    SGO_CUDA_OK(e, cudaGetLastError());
+    SGO_LAUNCHED(e);
     return 0;
 }
 
@@ -421,6 +424,6 @@ extern "C" int sgo_random_playouts(sgo_engine *e, int32_t first, int32_t n, uint
     RANGE_OK(e, first, n, e->G);
     if (n == 0) return 0;
     k_random_playouts<<<warp_grid(n), WARPS_PER_BLOCK * 32, 0, S_(stream)>>>(e->boards, e->S, first, n, seed, max_plies, d_moves, d_nplies);
-    SGO_CUDA_OK(e, cudaGetLastError());
+    SGO_LAUNCHED(e);
     return 0;
 }

@@ -43,7 +43,12 @@ struct sgo_tower {
     CUtensorMap map_w;
     int32_t *err;
     int sm_count;
+    // optional live profiling (bench.py roofline): 4 events per forward call
+    int prof_on, prof_n;
+    cudaEvent_t *prof_ev;          // [TW_PROF_MAX][4]: start, after stem, after convs, after heads
+    int *prof_pos;                 // positions in each profiled forward
 };
+#define TW_PROF_MAX 4096
 
 static inline cudaStream_t S_(void *s) { return (cudaStream_t)s; }
 
@@ -528,6 +533,11 @@ static void tower_free(sgo_tower *t)
     cudaFree(t->val_fc2_w); cudaFree(t->val_fc2_b);
     for (int i = 0; i < 3; i++) cudaFree(t->act[i]);
     cudaFree(t->err);
+    if (t->prof_ev) {
+        for (int i = 0; i < TW_PROF_MAX * 4; i++) cudaEventDestroy(t->prof_ev[i]);
+        delete[] t->prof_ev;
+        delete[] t->prof_pos;
+    }
     delete t;
 }
 
@@ -609,7 +619,7 @@ static int launch_conv(sgo_engine *e, sgo_tower *t, int n, int layer, int in, in
     a.err = t->err;
     int grid = a.n_tiles < t->sm_count ? a.n_tiles : t->sm_count;
     k_conv3x3_tc<<<grid, TW_THREADS, TW_SMEM_BYTES, S_(stream)>>>(t->map_act[in], t->map_w, a);
-    SGO_CUDA_OK(e, cudaGetLastError());
+    SGO_LAUNCHED(e);
     return 0;
 }
 
@@ -626,8 +636,12 @@ extern "C" int sgo_tower_forward(sgo_engine *e, int32_t slot, int32_t which, con
     const Board *boards = which ? e->leaf_boards : e->boards;
     int P = t->W * t->W;
     int grid = n < t->sm_count ? n : t->sm_count;
+    const bool prof = t->prof_on && t->prof_n < TW_PROF_MAX;
+    cudaEvent_t *pe = prof ? t->prof_ev + (size_t)t->prof_n * 4 : nullptr;
+    if (prof) cudaEventRecord(pe[0], S_(stream));
     k_stem<<<grid, TW_C, 9 * 16 * TW_C * sizeof(float), S_(stream)>>>(boards, d_index, d_sym, n, t->S, t->stem_w, t->stem_b, t->act[0]);
-    SGO_CUDA_OK(e, cudaGetLastError());
+    SGO_LAUNCHED(e);
+    if (prof) cudaEventRecord(pe[1], S_(stream));
     int x = 0;                                     // act[x] holds the block input
     for (int b = 0; b < t->n_blocks; b++) {
         int tmp = (x + 1) % 3, y = (x + 2) % 3;
@@ -637,6 +651,7 @@ extern "C" int sgo_tower_forward(sgo_engine *e, int32_t slot, int32_t which, con
         if (rc) return rc;
         x = y;
     }
+    if (prof) cudaEventRecord(pe[2], S_(stream));
     HeadArgs h;
     h.n = n; h.S = t->S; h.W = t->W; h.scatter = scatter; h.index = d_index; h.syms = d_sym; h.act = t->act[x];
     h.pcw = t->pol_conv_w; h.pcb = t->pol_conv_b; h.pfw = t->pol_fc_w; h.pfb = t->pol_fc_b;
@@ -646,7 +661,46 @@ extern "C" int sgo_tower_forward(sgo_engine *e, int32_t slot, int32_t which, con
     int hgrid = (n + HD_P - 1) / HD_P;
     if (hgrid > 4 * t->sm_count) hgrid = 4 * t->sm_count;
     k_heads<<<hgrid, HD_THREADS, hs, S_(stream)>>>(h);
-    SGO_CUDA_OK(e, cudaGetLastError());
+    SGO_LAUNCHED(e);
+    if (prof) { cudaEventRecord(pe[3], S_(stream)); t->prof_pos[t->prof_n++] = n; }
+    return 0;
+}
+
+// live kernel timing for the roofline figures: enable, run, then read (synchronises).
+// h_out[0..2] = total ms in stem / conv layers / heads, h_out[3] = conv kernel launches,
+// h_out[4] = positions evaluated, h_out[5] = forward calls profiled
+extern "C" int sgo_tower_profile(sgo_engine *e, int32_t slot, int32_t enable)
+{
+    if (slot < 0 || slot > 1 || !e->tower[slot]) return sgo_fail(e, "tower slot has no weights");
+    sgo_tower *t = e->tower[slot];
+    if (enable && !t->prof_ev) {
+        t->prof_ev = new cudaEvent_t[TW_PROF_MAX * 4];
+        t->prof_pos = new int[TW_PROF_MAX];
+        for (int i = 0; i < TW_PROF_MAX * 4; i++) SGO_CUDA_OK(e, cudaEventCreate(&t->prof_ev[i]));
+    }
+    t->prof_on = enable;
+    t->prof_n = 0;
+    return 0;
+}
+
+extern "C" int sgo_tower_profile_read_sync(sgo_engine *e, int32_t slot, double *h_out)
+{
+    if (slot < 0 || slot > 1 || !e->tower[slot]) return sgo_fail(e, "tower slot has no weights");
+    sgo_tower *t = e->tower[slot];
+    SGO_CUDA_OK(e, cudaDeviceSynchronize());
+    for (int i = 0; i < 6; i++) h_out[i] = 0;
+    for (int i = 0; i < t->prof_n; i++) {
+        cudaEvent_t *pe = t->prof_ev + (size_t)i * 4;
+        for (int k = 0; k < 3; k++) {
+            float ms = 0;
+            SGO_CUDA_OK(e, cudaEventElapsedTime(&ms, pe[k], pe[k + 1]));
+            h_out[k] += ms;
+        }
+        h_out[3] += t->n_layers;
+        h_out[4] += t->prof_pos[i];
+    }
+    h_out[5] = t->prof_n;
+    t->prof_n = 0;
     return 0;
 }
 

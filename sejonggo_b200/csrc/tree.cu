@@ -598,7 +598,7 @@ __global__ void k_leaf_compact(const LeafRef *leaf_refs, int total, int32_t *ind
 }
 
 // ------------------------------------------------------------------ C ABI
-#define LAUNCH_OK(e) SGO_CUDA_OK(e, cudaGetLastError())
+#define LAUNCH_OK(e) SGO_LAUNCHED(e)
 
 extern "C" int sgo_tree_reset(sgo_engine *e, void *stream)
 {

@@ -74,6 +74,9 @@ class Engine(object):
     def _p(t):
         return C.c_void_p(0 if t is None else t.data_ptr())
 
+    def launch_count(self):
+        return int(self.lib.sgo_launch_count(self.h))
+
     def check_errors(self):
         f = C.c_int32(0)
         self._ck(self.lib.sgo_check_errors_sync(self.h, self._stream(), C.byref(f)))

@@ -157,6 +157,15 @@ class TowerModel(object):
         if f.value:
             raise EngineError("tower kernel error flags 0x%x (16 = mbarrier wait timed out)" % f.value)
 
+    def profile(self, engine, slot=0, enable=True):
+        engine._ck(engine.lib.sgo_tower_profile(engine.h, slot, int(enable)))
+
+    def profile_read(self, engine, slot=0):
+        out = (C.c_double * 6)()
+        engine._ck(engine.lib.sgo_tower_profile_read_sync(engine.h, slot, out))
+        return dict(stem_ms=out[0], conv_ms=out[1], heads_ms=out[2], conv_launches=int(out[3]), positions=int(out[4]),
+                    forwards=int(out[5]))
+
     # ---- reference protocol (self_play.py:70,187) ----------------------------------
     def predict_on_batch(self, X):
         X = np.asarray(X)
