@@ -119,7 +119,70 @@ def cpu_selfplay(mode, plies_per_game, rounds=1):
     return dict(sims=plies * per, plies=plies, wall=wall, cores=cores)
 
 
-CPU_PLIES_PER_STEP = 10      # one CPU "step" = 10 plies of one game on every host core (~2 s of work per core)
+CPU_PLIES_PER_STEP = 10      # uniform-evaluator side measurement: 10 plies of one game on every host core
+
+
+class _CpuTower(object):
+    """The network of the SAME config on the host cores: oracle/tower_ref.py (fp32 torch restatement of
+    model.py:55-96) with all intra-op threads — the reference's CPU path includes evaluating its tower."""
+    name = "cpu_tower"
+
+    def __init__(self, blocks):
+        from sejonggo_b200 import model
+        self.params = model.init_params(SIZE, blocks, seed=0)
+        self.evals = 0
+
+    def predict_on_batch(self, X):
+        import numpy as np
+        import torch
+        from oracle import tower_ref
+        with torch.no_grad():
+            p, v = tower_ref.forward(self.params, np.asarray(X, dtype=np.float32))
+        self.evals += len(X)
+        return p.numpy(), v.numpy()
+
+
+def cpu_tower_selfplay(mode, blocks, warm, steps):
+    """One game on the host: W untimed + K timed search steps (mode A: one 100-leaf simulate batch;
+    mode B: one ENERGY=8 wave) through the oracle port with the CPU tower as evaluator."""
+    import numpy as np
+    import torch
+    from oracle import oracle as o, game_loop as gl
+    m = _CpuTower(blocks)
+    board, _ = o.game_init(SIZE)
+    p, _ = m.predict_on_batch(board)
+    tree = o.new_tree(p[0], board, noise=np.random.RandomState(0).dirichlet([0.03] * (SIZE * SIZE + 1)))
+    rng = gl.SeededRng(0)
+    per = BATCH_A if mode == 'a' else ENERGY_B
+
+    def one():
+        sym = rng.symmetry()
+        ev = lambda b: gl.sym_predict(m, b, sym)
+        if mode == 'a':
+            return o.simulate(tree, np.copy(board), ev, BATCH_A, 1)
+        return o.async_simulate2(tree, np.copy(board), ev, ENERGY_B, 1)
+
+    for _ in range(warm):
+        one()
+    t0 = time.time()
+    sims = sum(one() for _ in range(steps))
+    wall = time.time() - t0
+    return dict(sims=sims, wall=wall, cores=os.cpu_count() or 1, threads=torch.get_num_threads(), per=per)
+
+
+def _cpu_baseline_dict(mode, blocks, warm, steps, with_uniform=True):
+    r = cpu_tower_selfplay(mode, blocks, warm, steps)
+    cb = dict(value=r['sims'] / r['wall'], unit="simulations/s", cores=r['threads'], kind="port",
+              sample="1 game, %d timed %s of the same workload (19x19, %d-block tower evaluated in fp32 by torch on %d host threads, "
+                     "oracle C port for rules/tree); the reference's real evaluator was a TF1.7 GPU process"
+                     % (steps, "100-leaf simulate batches (mode A)" if mode == 'a' else "8-leaf waves (mode B)", blocks, r['threads']))
+    if with_uniform:
+        cpu_selfplay(mode, 1)
+        c = cpu_selfplay(mode, CPU_PLIES_PER_STEP)
+        cb["rules_tree_only"] = dict(value=c['sims'] / c['wall'], unit="simulations/s", cores=c['cores'],
+                                     note="free uniform evaluator (network cost excluded), one game per core, C oracle port; "
+                                          "the pure-Python reference measured 179 sims/s/core in the survey container")
+    return cb, r
 
 
 def run_reference(a):
@@ -127,20 +190,15 @@ def run_reference(a):
     if rank != 0:
         return
     steps, warm = max(1, a.steps), a.warmup
-    cpu_selfplay(a.mode, max(1, min(warm, 3)))                  # untimed warm-up (builds/loads the oracle, forks once)
-    plies = CPU_PLIES_PER_STEP * steps
-    r = cpu_selfplay(a.mode, plies)
-    val = r['sims'] / r['wall']
-    cb = dict(value=val, unit="simulations/s", cores=r['cores'], kind="port",
-              sample="%d games (one per core) x %d plies, 19x19, %d sims/ply, mode %s, uniform evaluator (network cost excluded); "
-                     "C oracle port of the pure-Python reference, which itself measured 179 sims/s/core in the survey container"
-                     % (r['cores'], plies, SIMS, a.mode.upper()))
+    cb, r = _cpu_baseline_dict(a.mode, a.blocks, warm, steps, with_uniform=False)
+    val = cb['value']
     print(json.dumps(dict(
         impl="reference", metric="selfplay_mcts_simulations_per_sec", value=val, unit="simulations/s", n_gpus=a.gpus,
         steps=steps, warmup=warm, ms_per_step=1e3 * r['wall'] / steps, higher_is_better=True, scaling="weak",
         vs_baseline=None, dtype="f32", data="synthetic",
-        config=dict(workload="19x19 self-play, %d sims/ply, mode %s, one game per host core" % (SIMS, a.mode.upper()),
-                    moves_per_sec=r['plies'] / r['wall'], step="%d plies of one game per core" % CPU_PLIES_PER_STEP),
+        config=dict(workload="19x19 self-play, conf.py default tower (%d blocks x 256 ch, random init), %d sims/ply, mode %s, "
+                             "1 game on all host cores" % (a.blocks, SIMS, a.mode.upper()),
+                    moves_per_sec=val / SIMS, step="one %d-leaf search step of one game" % r['per']),
         cpu_baseline=cb, e2e=dict(value=val, unit="simulations/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
 
 
@@ -239,12 +297,7 @@ def run_ours(a):
                       share_of_step=prof['conv_ms'] / r['ms'], stem_ms=prof['stem_ms'], heads_ms=prof['heads_ms']),
     )
     if world == 1 and not a.no_cpu:
-        cpu_selfplay(a.mode, 1)
-        c = cpu_selfplay(a.mode, 20)
-        out["cpu_baseline"] = dict(
-            value=c['sims'] / c['wall'], unit="simulations/s", cores=c['cores'], kind="port",
-            sample="%d games (one per core) x 20 plies, 19x19, %d sims/ply, mode %s, uniform evaluator (network cost excluded), C oracle port"
-                   % (c['cores'], SIMS, a.mode.upper()))
+        out["cpu_baseline"], _ = _cpu_baseline_dict(a.mode, a.blocks, 1, 2)
     print(json.dumps(out))
 
 
