@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 
 #define TW_C 256
@@ -29,6 +30,7 @@
 #define TW_TILE_BYTES (256 * 128)
 #define TW_THREADS 192
 #define TW_SPIN_LIMIT (1u << 21)
+#define TW_STEM_K 192                      // 9 taps x 17 planes = 153, padded to 3 x 64
 
 struct sgo_tower {
     int n_blocks, S, W, RT, max_pos, YB;
@@ -41,6 +43,10 @@ struct sgo_tower {
     __nv_bfloat16 *act[3];                  // [YB][W][C]
     CUtensorMap map_act[3];
     CUtensorMap map_w;
+    struct PairMaps *pmaps;                 // [3] tensor maps of the CTA-pair kernel (conv_pair.cuh); [3] = stem im2col
+    __nv_bfloat16 *stem_col;                // [YB][W][TW_STEM_K] im2col of the input planes (0/1, +-1)
+    __nv_bfloat16 *stem_wb;                 // [C co][TW_STEM_K] bf16 stem weights, k = tap*17 + plane
+    int f0, p0, f1, use_pair;
     int32_t *err;
     int sm_count;
     // optional live profiling (bench.py roofline): 4 events per forward call
@@ -130,6 +136,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
 
 struct ConvArgs {
     int W, RT, rows_per_pos, YB, n_tiles, w_row0, relu;
+    int variant;              // profiling experiments only: 1 = skip B loads, 2 = skip A loads, 4 = skip epilogue global traffic
     const float *bias;
     const __nv_bfloat16 *skip;
     __nv_bfloat16 *out;
@@ -185,6 +192,14 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__
                         ok = mbar_wait(&tail->empty[stage], phase ^ 1, a.err);
                         if (!ok) break;
                         uint8_t *sa = smem + (size_t)stage * 2 * TW_TILE_BYTES, *sb = sa + TW_TILE_BYTES;
+                        if (a.variant & 3) {          // experiments: drop one or both operand loads
+                            uint32_t bytes = ((a.variant & 2) ? 0u : a_box_bytes) + ((a.variant & 1) ? 0u : (uint32_t)TW_TILE_BYTES);
+                            if (bytes) mbar_expect_tx(&tail->full[stage], bytes); else mbar_arrive(&tail->full[stage]);
+                            if (!(a.variant & 2)) tma_load_3d(sa, &map_in, kc * TW_KCH, dx, yb0 + dy, &tail->full[stage]);
+                            if (!(a.variant & 1)) tma_load_2d(sb, &map_w, kc * TW_KCH, a.w_row0 + tap * TW_C, &tail->full[stage]);
+                            if (++stage == TW_STAGES) { stage = 0; phase ^= 1; }
+                            continue;
+                        }
                         mbar_expect_tx(&tail->full[stage], a_box_bytes + TW_TILE_BYTES);
                         tma_load_3d(sa, &map_in, kc * TW_KCH, dx, yb0 + dy, &tail->full[stage]);
                         tma_load_2d(sb, &map_w, kc * TW_KCH, a.w_row0 + tap * TW_C, &tail->full[stage]);
@@ -240,7 +255,7 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__
                 for (int c = 0; c < TW_C / 32; c++) {
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + h * 256 + c * 32, v);
-                    if (valid) {
+                    if (valid && !(a.variant & 4)) {
                         uint4 sk[4];
                         if (a.skip) {
                             const uint4 *sp = reinterpret_cast<const uint4 *>(a.skip + gofs + c * 32);
@@ -280,6 +295,8 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
 }
+
+#include "conv_pair.cuh"
 
 // ------------------------------------------------------------------ stem
 __device__ __forceinline__ void sym_src_t(int S, int sym, int y, int x, int &sy, int &sx)
@@ -351,6 +368,70 @@ k_stem(const Board *boards, const int32_t *index, const int32_t *syms, int n, in
             }
         __syncthreads();
     }
+}
+
+// Stem as a tensor-core GEMM: im2col of the (symmetry-transformed) input planes straight from
+// the packed bitboards: col[row(y), x][tap*17 + p] = plane p at (y+ky, x+kx)  (valid conv, Q11).
+// Every value is 0, 1 or +-1, exact in bf16.  One 16-B store per thread-item (8 k's).
+__global__ void __launch_bounds__(256)
+k_stem_im2col(const Board *boards, const int32_t *index, const int32_t *syms, int n, int S, __nv_bfloat16 *col)
+{
+    __shared__ uint16_t cell[SGO_MAXS * SGO_MAXS];
+    __shared__ int s_tm;
+    const int W = S - 2, items_per_px = TW_STEM_K / 8;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int src = index ? index[i] : i;
+        __syncthreads();
+        if (src < 0) continue;
+        const Board *bd = boards + src;
+        const int sym = syms ? (syms[i] & 7) : 0;
+        const int tm = bd->to_move, head = bd->head;
+        for (int c = threadIdx.x; c < S * S; c += blockDim.x) {
+            int y = c / S, x = c - y * S, sy, sx;
+            sym_src_t(S, sym, y, x, sy, sx);
+            uint32_t m = 0;
+#pragma unroll
+            for (int k = 0; k < SGO_HIST; k++) {
+                int slot = (head + SGO_HIST - k) & (SGO_HIST - 1);
+                uint32_t bl = (bd->st[slot][0][sy] >> sx) & 1u, wh = (bd->st[slot][1][sy] >> sx) & 1u;
+                uint32_t own = tm == 1 ? bl : wh, opp = tm == 1 ? wh : bl;
+                m |= (own << (2 * k)) | (opp << (2 * k + 1));
+            }
+            cell[c] = (uint16_t)m;
+        }
+        if (threadIdx.x == 0) s_tm = tm;
+        __syncthreads();
+        const uint16_t one = 0x3F80, tmv = s_tm == 1 ? 0x3F80 : 0xBF80;       // bf16 +1 / -1
+        const size_t row0 = (size_t)i * (W + 1) + 1;
+        for (int it = threadIdx.x; it < W * W * items_per_px; it += blockDim.x) {
+            int px = it / items_per_px, k0 = (it - px * items_per_px) * 8;
+            int y = px / W, x = px - y * W;
+            uint16_t v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                int k = k0 + j, tap = k / 17, p = k - tap * 17;
+                uint16_t val = 0;
+                if (k < 153) {
+                    if (p == 16) val = tmv;
+                    else val = ((cell[(y + tap / 3) * S + x + tap % 3] >> p) & 1u) ? one : (uint16_t)0;
+                }
+                v[j] = val;
+            }
+            uint4 o;
+            o.x = v[0] | ((uint32_t)v[1] << 16); o.y = v[2] | ((uint32_t)v[3] << 16);
+            o.z = v[4] | ((uint32_t)v[5] << 16); o.w = v[6] | ((uint32_t)v[7] << 16);
+            *reinterpret_cast<uint4 *>(col + ((row0 + y) * W + x) * TW_STEM_K + k0) = o;
+        }
+    }
+}
+
+// fp32 [9][17][C] stem weights (BN folded) -> bf16 [C][TW_STEM_K]
+__global__ void k_stem_weights(const float *w, __nv_bfloat16 *wb)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= TW_C * TW_STEM_K) return;
+    int co = i / TW_STEM_K, k = i - co * TW_STEM_K;
+    wb[i] = __float2bfloat16(k < 153 ? w[(size_t)k * TW_C + co] : 0.f);
 }
 
 // ------------------------------------------------------------------ heads
@@ -521,6 +602,57 @@ static int make_maps(sgo_engine *e, sgo_tower *t)
     CUresult r = enc(&t->map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, t->conv_w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(weights) failed");
+    // CTA-pair kernel: rank 0 = f0 full rows + p0 pixels, rank 1 = (W-p0) pixels + f1 full rows
+    t->f0 = 128 / t->W;
+    t->p0 = 128 - t->f0 * t->W;
+    t->f1 = t->RT - t->f0 - (t->p0 ? 1 : 0);
+    t->pmaps = new PairMaps[4];
+    for (int i = 0; i < 3; i++) {
+        cuuint64_t dims3[3] = {(cuuint64_t)TW_C, (cuuint64_t)t->W, (cuuint64_t)t->YB};
+        cuuint64_t str3[2] = {(cuuint64_t)TW_C * 2, (cuuint64_t)TW_C * 2 * t->W};
+        cuuint32_t es3[3] = {1, 1, 1};
+        struct { CUtensorMap *m; cuuint32_t bx, by; } boxes[4] = {
+            {&t->pmaps[i].full0, (cuuint32_t)t->W, (cuuint32_t)t->f0},
+            {&t->pmaps[i].part0, (cuuint32_t)(t->p0 ? t->p0 : 1), 1},
+            {&t->pmaps[i].part1, (cuuint32_t)(t->p0 ? t->W - t->p0 : 1), 1},
+            {&t->pmaps[i].full1, (cuuint32_t)t->W, (cuuint32_t)(t->f1 ? t->f1 : 1)}};
+        for (int b = 0; b < 4; b++) {
+            cuuint32_t box3[3] = {TW_KCH, boxes[b].bx, boxes[b].by};
+            CUresult rr = enc(boxes[b].m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, t->act[i], dims3, str3, box3, es3,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (rr != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(pair activations) failed");
+        }
+        cuuint32_t boxw[2] = {TW_KCH, 128};
+        CUresult rr = enc(&t->pmaps[i].w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, t->conv_w, dims, strides, boxw, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rr != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(pair weights) failed");
+    }
+    {   // stem GEMM: A = im2col tensor (K = TW_STEM_K), B = bf16 stem weights
+        cuuint64_t dims3[3] = {(cuuint64_t)TW_STEM_K, (cuuint64_t)t->W, (cuuint64_t)t->YB};
+        cuuint64_t str3[2] = {(cuuint64_t)TW_STEM_K * 2, (cuuint64_t)TW_STEM_K * 2 * t->W};
+        cuuint32_t es3[3] = {1, 1, 1};
+        struct { CUtensorMap *m; cuuint32_t bx, by; } boxes[4] = {
+            {&t->pmaps[3].full0, (cuuint32_t)t->W, (cuuint32_t)t->f0},
+            {&t->pmaps[3].part0, (cuuint32_t)(t->p0 ? t->p0 : 1), 1},
+            {&t->pmaps[3].part1, (cuuint32_t)(t->p0 ? t->W - t->p0 : 1), 1},
+            {&t->pmaps[3].full1, (cuuint32_t)t->W, (cuuint32_t)(t->f1 ? t->f1 : 1)}};
+        for (int b = 0; b < 4; b++) {
+            cuuint32_t box3[3] = {TW_KCH, boxes[b].bx, boxes[b].by};
+            CUresult rr = enc(boxes[b].m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, t->stem_col, dims3, str3, box3, es3,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (rr != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(stem im2col) failed");
+        }
+        cuuint64_t dw[2] = {(cuuint64_t)TW_STEM_K, (cuuint64_t)TW_C};
+        cuuint64_t sw_[1] = {(cuuint64_t)TW_STEM_K * 2};
+        cuuint32_t boxw[2] = {TW_KCH, 128};
+        CUresult rr = enc(&t->pmaps[3].w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, t->stem_wb, dw, sw_, boxw, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rr != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(stem weights) failed");
+    }
     return 0;
 }
 
@@ -533,6 +665,8 @@ static void tower_free(sgo_tower *t)
     cudaFree(t->val_fc2_w); cudaFree(t->val_fc2_b);
     for (int i = 0; i < 3; i++) cudaFree(t->act[i]);
     cudaFree(t->err);
+    cudaFree(t->stem_col); cudaFree(t->stem_wb);
+    delete[] t->pmaps;
     if (t->prof_ev) {
         for (int i = 0; i < TW_PROF_MAX * 4; i++) cudaEventDestroy(t->prof_ev[i]);
         delete[] t->prof_ev;
@@ -590,12 +724,23 @@ extern "C" int sgo_tower_load_weights(sgo_engine *e, int32_t slot, const sgo_tow
         SGO_CUDA_OK(e, cudaMalloc(&t->act[i], act_bytes));
         SGO_CUDA_OK(e, cudaMemsetAsync(t->act[i], 0, act_bytes, S_(stream)));     // pad rows stay zero forever
     }
+    size_t col_bytes = (size_t)t->YB * t->W * TW_STEM_K * sizeof(__nv_bfloat16);
+    SGO_CUDA_OK(e, cudaMalloc(&t->stem_col, col_bytes));
+    SGO_CUDA_OK(e, cudaMemsetAsync(t->stem_col, 0, col_bytes, S_(stream)));
+    SGO_CUDA_OK(e, cudaMalloc(&t->stem_wb, sizeof(__nv_bfloat16) * TW_C * TW_STEM_K));
+    k_stem_weights<<<(TW_C * TW_STEM_K + 255) / 256, 256, 0, S_(stream)>>>(t->stem_w, t->stem_wb);
+    SGO_CUDA_OK(e, cudaGetLastError());
     SGO_CUDA_OK(e, cudaMalloc(&t->err, sizeof(int32_t)));
     SGO_CUDA_OK(e, cudaMemsetAsync(t->err, 0, sizeof(int32_t), S_(stream)));
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev);
     SGO_CUDA_OK(e, cudaFuncSetAttribute(k_conv3x3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM_BYTES));
+    SGO_CUDA_OK(e, cudaFuncSetAttribute(k_conv3x3_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM_BYTES));
+    {
+        const char *v = getenv("SGO_CONV_SINGLE");            // debugging switch: force the single-CTA kernel
+        t->use_pair = !(v && v[0] == '1');
+    }
     SGO_CUDA_OK(e, cudaFuncSetAttribute(k_stem, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 16 * TW_C * (int)sizeof(float)));
     int hs = (HD_P * (4 * P + A + 256) + TW_C * 4) * (int)sizeof(float);
     SGO_CUDA_OK(e, cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, hs));
@@ -605,9 +750,12 @@ extern "C" int sgo_tower_load_weights(sgo_engine *e, int32_t slot, const sgo_tow
     return 0;
 }
 
+static int g_conv_variant = 0;
+
 static int launch_conv(sgo_engine *e, sgo_tower *t, int n, int layer, int in, int out, int skip, void *stream)
 {
     ConvArgs a;
+    a.variant = g_conv_variant;
     a.W = t->W; a.RT = t->RT; a.rows_per_pos = t->W + 1;
     a.YB = n * (t->W + 1) + 1;
     a.n_tiles = (a.YB + t->RT - 1) / t->RT;
@@ -617,6 +765,17 @@ static int launch_conv(sgo_engine *e, sgo_tower *t, int n, int layer, int in, in
     a.skip = skip >= 0 ? t->act[skip] : nullptr;
     a.out = t->act[out];
     a.err = t->err;
+    if (t->use_pair && !g_conv_variant) {
+        PairArgs pa;
+        pa.W = a.W; pa.RT = a.RT; pa.rows_per_pos = a.rows_per_pos; pa.YB = a.YB; pa.n_tiles = a.n_tiles; pa.w_row0 = a.w_row0;
+        pa.n_taps = 9; pa.kchunks = TW_C / TW_KCH;
+        pa.relu = 1; pa.f0 = t->f0; pa.p0 = t->p0; pa.f1 = t->f1; pa.bias = a.bias; pa.skip = a.skip; pa.out = a.out; pa.err = a.err;
+        int pairs = t->sm_count / 2;
+        if (pairs > a.n_tiles) pairs = a.n_tiles;
+        k_conv3x3_pair<<<2 * pairs, TW_THREADS, PR_SMEM_BYTES, S_(stream)>>>(t->pmaps[in], pa);
+        SGO_LAUNCHED(e);
+        return 0;
+    }
     int grid = a.n_tiles < t->sm_count ? a.n_tiles : t->sm_count;
     k_conv3x3_tc<<<grid, TW_THREADS, TW_SMEM_BYTES, S_(stream)>>>(t->map_act[in], t->map_w, a);
     SGO_LAUNCHED(e);
@@ -639,8 +798,23 @@ extern "C" int sgo_tower_forward(sgo_engine *e, int32_t slot, int32_t which, con
     const bool prof = t->prof_on && t->prof_n < TW_PROF_MAX;
     cudaEvent_t *pe = prof ? t->prof_ev + (size_t)t->prof_n * 4 : nullptr;
     if (prof) cudaEventRecord(pe[0], S_(stream));
-    k_stem<<<grid, TW_C, 9 * 16 * TW_C * sizeof(float), S_(stream)>>>(boards, d_index, d_sym, n, t->S, t->stem_w, t->stem_b, t->act[0]);
-    SGO_LAUNCHED(e);
+    if (t->use_pair) {
+        // stem = im2col from the bitboards + one pair-kernel GEMM (K = 192) with the bias/ReLU epilogue
+        int g2 = n < 8 * t->sm_count ? n : 8 * t->sm_count;
+        k_stem_im2col<<<g2, 256, 0, S_(stream)>>>(boards, d_index, d_sym, n, t->S, t->stem_col);
+        SGO_LAUNCHED(e);
+        PairArgs pa;
+        pa.W = t->W; pa.RT = t->RT; pa.rows_per_pos = t->W + 1; pa.YB = n * (t->W + 1) + 1;
+        pa.n_tiles = (pa.YB + t->RT - 1) / t->RT; pa.w_row0 = 0; pa.relu = 1; pa.n_taps = 1; pa.kchunks = TW_STEM_K / TW_KCH;
+        pa.f0 = t->f0; pa.p0 = t->p0; pa.f1 = t->f1; pa.bias = t->stem_b; pa.skip = nullptr; pa.out = t->act[0]; pa.err = t->err;
+        int pairs = t->sm_count / 2;
+        if (pairs > pa.n_tiles) pairs = pa.n_tiles;
+        k_conv3x3_pair<<<2 * pairs, TW_THREADS, PR_SMEM_BYTES, S_(stream)>>>(t->pmaps[3], pa);
+        SGO_LAUNCHED(e);
+    } else {
+        k_stem<<<grid, TW_C, 9 * 16 * TW_C * sizeof(float), S_(stream)>>>(boards, d_index, d_sym, n, t->S, t->stem_w, t->stem_b, t->act[0]);
+        SGO_LAUNCHED(e);
+    }
     if (prof) cudaEventRecord(pe[1], S_(stream));
     int x = 0;                                     // act[x] holds the block input
     for (int b = 0; b < t->n_blocks; b++) {
@@ -721,9 +895,13 @@ extern "C" int sgo_tower_debug_conv(sgo_engine *e, int32_t slot, int32_t n, int3
 {
     if (slot < 0 || slot > 1 || !e->tower[slot]) return sgo_fail(e, "tower slot has no weights");
     sgo_tower *t = e->tower[slot];
-    if (n < 1 || n > t->max_pos || layer < 0 || layer >= t->n_layers || in < 0 || in > 2 || out < 0 || out > 2 || skip > 2)
+    if (n < 1 || n > t->max_pos || layer < 0 || layer >= t->n_layers || in < 0 || in > 2 || out < 0 || out > 2 || (skip > 2 && skip < 16))
         return sgo_fail(e, "debug_conv arguments out of range");
-    return launch_conv(e, t, n, layer, in, out, skip, stream);
+    g_conv_variant = skip >= 16 ? (skip >> 4) : 0;      // profiling experiments: variant flags ride in skip's high bits
+    if (skip >= 16) skip = (skip & 15) == 15 ? -1 : (skip & 15);
+    int rc = launch_conv(e, t, n, layer, in, out, skip, stream);
+    g_conv_variant = 0;
+    return rc;
 }
 
 // raw activation buffer access (bf16 [n*(W+1)+1][W][C]) for tests

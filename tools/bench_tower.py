@@ -38,10 +38,19 @@ def main():
     flop_layer = 2.0 * n * 289 * 256 * 256 * 9
     t_fwd = timed(lambda: e._ck(e.lib.sgo_tower_forward(e.h, 0, 0, C.c_void_p(idx.data_ptr()), n, C.c_void_p(0), 0,
                                                          C.c_void_p(pol.data_ptr()), C.c_void_p(val.data_ptr()), e._stream())), iters=3, warm=1)
+    m.profile(e, 0, True)
+    import subprocess, threading
+    clk = []
+    pr = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+    threading.Thread(target=lambda: [clk.append(l.strip()) for l in pr.stdout], daemon=True).start()
+    t_sus = timed(lambda: e._ck(e.lib.sgo_tower_forward(e.h, 0, 0, C.c_void_p(idx.data_ptr()), n, C.c_void_p(0), 0,
+                                                         C.c_void_p(pol.data_ptr()), C.c_void_p(val.data_ptr()), e._stream())), iters=20, warm=0)
+    pr.terminate()
+    prof = m.profile_read(e, 0)
     m.check(e, 0)
     flop_fwd = n * (2.0 * 289 * 256 * 256 * 9 * 2 * blocks + 2.0 * 289 * 9 * 17 * 256 + 1.3e6)
     print(json.dumps(dict(n=n, blocks=blocks, conv_layer_s=t_conv, conv_layer_tflops=flop_layer / t_conv / 1e12,
-                          forward_s=t_fwd, forward_tflops=flop_fwd / t_fwd / 1e12, evals_per_s=n / t_fwd)))
+                          forward_s=t_fwd, sustained_forward_s=t_sus, prof_per_forward_ms={k: (v / prof['forwards'] if k.endswith('_ms') else v) for k, v in prof.items()}, clocks=clk[::4], forward_tflops=flop_fwd / t_fwd / 1e12, evals_per_s=n / t_fwd)))
 
 
 if __name__ == "__main__":
