@@ -33,8 +33,12 @@ struct PairArgs {
     int f0, p0, f1;           // rank 0: f0 full rows + p0 pixels of row f0; rank 1: (W-p0) pixels of row f0 (if p0) + f1 full rows
     const float *bias;
     const __nv_bfloat16 *skip;
-    __nv_bfloat16 *out;
+    __nv_bfloat16 *out;       // nullptr: do not store the activations (last layer feeding only the heads)
     int32_t *err;
+    // fused 1x1 head convolutions (model.py:73,83) on the last layer: feat[(pos*W*W + pix)*4 + {p0,p1,v0,v1}]
+    const float *head_w4;     // [C][4] folded weights, nullptr = off
+    const float *head_b4;     // [4]
+    float *feat;
 };
 
 struct PairSmemTail {
@@ -42,6 +46,7 @@ struct PairSmemTail {
     uint32_t tmem_base;
     uint32_t pad;
     float bias[TW_C];
+    float4 w4[TW_C];
 };
 #define PR_SMEM_BYTES (PR_STAGES * PR_STAGE_BYTES + (int)sizeof(PairSmemTail) + 1024)
 
@@ -116,7 +121,10 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tail->tmem_base)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < TW_C; i += blockDim.x) tail->bias[i] = a.bias[i];
+    for (int i = threadIdx.x; i < TW_C; i += blockDim.x) {
+        tail->bias[i] = a.bias[i];
+        if (a.head_w4) tail->w4[i] = reinterpret_cast<const float4 *>(a.head_w4)[i];
+    }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                       // peer barriers are initialised before anyone signals them
@@ -197,6 +205,7 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
             ok = __all_sync(SGO_FULL, ok);
             if (!ok) break;
             tc_fence_after();
+            float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
 #pragma unroll 1
             for (int c = 0; c < TW_C / 32; c++) {
                 uint4 sk[4];
@@ -223,14 +232,28 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
                         if (a.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
                         __nv_bfloat162 p = __floats2bfloat162_rn(f0, f1);
                         ow[j] = *reinterpret_cast<uint32_t *>(&p);
+                        if (a.head_w4) {
+                            float4 wa = tail->w4[c * 32 + 2 * j], wb = tail->w4[c * 32 + 2 * j + 1];
+                            h0 = fmaf(f0, wa.x, h0); h1 = fmaf(f0, wa.y, h1); h2 = fmaf(f0, wa.z, h2); h3 = fmaf(f0, wa.w, h3);
+                            h0 = fmaf(f1, wb.x, h0); h1 = fmaf(f1, wb.y, h1); h2 = fmaf(f1, wb.z, h2); h3 = fmaf(f1, wb.w, h3);
+                        }
                     }
-                    uint4 *op = reinterpret_cast<uint4 *>(a.out + gofs + c * 32);
+                    if (a.out) {
+                        uint4 *op = reinterpret_cast<uint4 *>(a.out + gofs + c * 32);
 #pragma unroll
-                    for (int j = 0; j < 4; j++) op[j] = o[j];
+                        for (int j = 0; j < 4; j++) op[j] = o[j];
+                    }
                 }
             }
             tc_fence_before();
             mbar_arrive_leader(&tail->tmem_empty[acc]);
+            if (valid && a.head_w4) {
+                int pos = (yb - 1) / a.rows_per_pos, y = (yb - 1) - pos * a.rows_per_pos;
+                float4 r4;
+                r4.x = fmaxf(h0 + a.head_b4[0], 0.f); r4.y = fmaxf(h1 + a.head_b4[1], 0.f);
+                r4.z = fmaxf(h2 + a.head_b4[2], 0.f); r4.w = fmaxf(h3 + a.head_b4[3], 0.f);
+                reinterpret_cast<float4 *>(a.feat)[((size_t)pos * a.W + y) * a.W + x] = r4;
+            }
         }
     }
     tc_fence_before();

@@ -46,6 +46,7 @@ struct sgo_tower {
     struct PairMaps *pmaps;                 // [3] tensor maps of the CTA-pair kernel (conv_pair.cuh); [3] = stem im2col
     __nv_bfloat16 *stem_col;                // [YB][W][TW_STEM_K] im2col of the input planes (0/1, +-1)
     __nv_bfloat16 *stem_wb;                 // [C co][TW_STEM_K] bf16 stem weights, k = tap*17 + plane
+    float *head_w4, *head_b4, *feat;        // fused 1x1 head convs: [C][4], [4]; features [max_pos][W*W][4]
     int f0, p0, f1, use_pair;
     int32_t *err;
     int sm_count;
@@ -425,6 +426,17 @@ k_stem_im2col(const Board *boards, const int32_t *index, const int32_t *syms, in
     }
 }
 
+// 1x1 head conv weights [C][2] + [C][2] -> interleaved [C][4] (p0,p1,v0,v1) and biases [4]
+__global__ void k_head_w4(const float *pcw, const float *pcb, const float *vcw, const float *vcb, float *w4, float *b4)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < TW_C) {
+        w4[c * 4 + 0] = pcw[c * 2]; w4[c * 4 + 1] = pcw[c * 2 + 1];
+        w4[c * 4 + 2] = vcw[c * 2]; w4[c * 4 + 3] = vcw[c * 2 + 1];
+    }
+    if (c < 2) { b4[c] = pcb[c]; b4[2 + c] = vcb[c]; }
+}
+
 // fp32 [9][17][C] stem weights (BN folded) -> bf16 [C][TW_STEM_K]
 __global__ void k_stem_weights(const float *w, __nv_bfloat16 *wb)
 {
@@ -564,6 +576,123 @@ k_heads(HeadArgs h)
     }
 }
 
+// Dense heads on the fused 1x1-conv features (feat[pos][pix][p0,p1,v0,v1], fp32, post BN+ReLU):
+// policy Dense(2P -> A) + softmax, value Dense(2P -> 256) + ReLU + Dense(256 -> 1) + tanh
+// (model.py:77-92).  A CTA owns FC_PB positions per pass: features sit transposed in shared
+// memory ([feature][position]) so one LDS.128 feeds 4 FMAs, and every weight is read once per
+// FC_PB positions (coalesced over the output index).
+#define FC_PB 16
+#define FC_THREADS 256
+
+struct FcArgs {
+    int n, S, W, scatter;
+    const int32_t *index, *syms;
+    const float *feat;
+    const float *pfw, *pfb, *v1w, *v1b, *v2w, *v2b;
+    float *policy, *value;
+};
+
+__global__ void __launch_bounds__(FC_THREADS)
+k_heads_fc(FcArgs h)
+{
+    extern __shared__ float fs[];
+    const int W = h.W, P = W * W, A = h.S * h.S + 1;
+    float *sfeat = fs;                               // [4P][FC_PB]
+    float *logit = sfeat + (size_t)4 * P * FC_PB;    // [FC_PB][A]
+    float *vpart = logit + FC_PB * A;                // [FC_PB][FC_THREADS/32]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int base = blockIdx.x * FC_PB; base < h.n; base += gridDim.x * FC_PB) {
+        const int np = min(FC_PB, h.n - base);
+        __syncthreads();
+        for (int t = threadIdx.x; t < 4 * P * FC_PB; t += blockDim.x) {
+            int p = t / (4 * P), f = t - p * 4 * P;               // coalesced read of position p's features
+            sfeat[f * FC_PB + p] = p < np ? h.feat[(size_t)(base + p) * 4 * P + f] : 0.f;
+        }
+        __syncthreads();
+        for (int a0 = threadIdx.x; a0 < A; a0 += blockDim.x) {      // policy logits
+            float acc[FC_PB];
+            const float b = h.pfb[a0];
+#pragma unroll
+            for (int p = 0; p < FC_PB; p++) acc[p] = b;
+            for (int pix = 0; pix < P; pix++) {
+#pragma unroll
+                for (int ch = 0; ch < 2; ch++) {
+                    const float wv = h.pfw[(size_t)(pix * 2 + ch) * A + a0];       // flatten order HWC
+                    const float4 *f4 = reinterpret_cast<const float4 *>(sfeat + (pix * 4 + ch) * FC_PB);
+#pragma unroll
+                    for (int q = 0; q < FC_PB / 4; q++) {
+                        float4 f = f4[q];
+                        acc[4 * q] = fmaf(f.x, wv, acc[4 * q]); acc[4 * q + 1] = fmaf(f.y, wv, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(f.z, wv, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(f.w, wv, acc[4 * q + 3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < FC_PB; p++) logit[p * A + a0] = acc[p];
+        }
+        {                                                           // value hidden layer, thread = unit
+            const int j = threadIdx.x;
+            float acc[FC_PB];
+            const float b = h.v1b[j];
+#pragma unroll
+            for (int p = 0; p < FC_PB; p++) acc[p] = b;
+            for (int pix = 0; pix < P; pix++) {
+#pragma unroll
+                for (int ch = 0; ch < 2; ch++) {
+                    const float wv = h.v1w[(size_t)(pix * 2 + ch) * 256 + j];
+                    const float4 *f4 = reinterpret_cast<const float4 *>(sfeat + (pix * 4 + 2 + ch) * FC_PB);
+#pragma unroll
+                    for (int q = 0; q < FC_PB / 4; q++) {
+                        float4 f = f4[q];
+                        acc[4 * q] = fmaf(f.x, wv, acc[4 * q]); acc[4 * q + 1] = fmaf(f.y, wv, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(f.z, wv, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(f.w, wv, acc[4 * q + 3]);
+                    }
+                }
+            }
+            const float w2 = h.v2w[j];
+#pragma unroll
+            for (int p = 0; p < FC_PB; p++) {
+                float v = fmaxf(acc[p], 0.f) * w2;
+                for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(SGO_FULL, v, o);
+                if (lane == 0) vpart[p * (FC_THREADS / 32) + warp] = v;
+            }
+        }
+        __syncthreads();
+        // softmax + outputs: one warp per position (2 positions per warp)
+        for (int p = warp; p < np; p += FC_THREADS / 32) {
+            float mx = -3.4e38f;
+            for (int a0 = lane; a0 < A; a0 += 32) mx = fmaxf(mx, logit[p * A + a0]);
+            for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(SGO_FULL, mx, o));
+            float sum = 0.f;
+            for (int a0 = lane; a0 < A; a0 += 32) {
+                float ev = expf(logit[p * A + a0] - mx);
+                logit[p * A + a0] = ev;
+                sum += ev;
+            }
+            for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(SGO_FULL, sum, o);
+            __syncwarp();
+            const int i = base + p;
+            const size_t orow = h.scatter ? (size_t)(h.index ? h.index[i] : i) : (size_t)i;
+            const int sym = h.syms ? (h.syms[i] & 7) : 0;
+            const float inv = 1.f / sum;
+            for (int a0 = lane; a0 < A; a0 += 32) {
+                int src = a0;
+                if (a0 < h.S * h.S) {                               // "reverse" gather re-uses the forward map (Q8)
+                    int y = a0 / h.S, x = a0 - y * h.S, sy, sx;
+                    sym_src_t(h.S, sym, y, x, sy, sx);
+                    src = sy * h.S + sx;
+                }
+                h.policy[orow * A + a0] = logit[p * A + src] * inv;
+            }
+            if (lane == 0) {
+                float vs = h.v2b[0];
+                for (int w8 = 0; w8 < FC_THREADS / 32; w8++) vs += vpart[p * (FC_THREADS / 32) + w8];
+                h.value[orow] = tanhf(vs);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -665,7 +794,7 @@ static void tower_free(sgo_tower *t)
     cudaFree(t->val_fc2_w); cudaFree(t->val_fc2_b);
     for (int i = 0; i < 3; i++) cudaFree(t->act[i]);
     cudaFree(t->err);
-    cudaFree(t->stem_col); cudaFree(t->stem_wb);
+    cudaFree(t->stem_col); cudaFree(t->stem_wb); cudaFree(t->head_w4); cudaFree(t->head_b4); cudaFree(t->feat);
     delete[] t->pmaps;
     if (t->prof_ev) {
         for (int i = 0; i < TW_PROF_MAX * 4; i++) cudaEventDestroy(t->prof_ev[i]);
@@ -730,6 +859,13 @@ extern "C" int sgo_tower_load_weights(sgo_engine *e, int32_t slot, const sgo_tow
     SGO_CUDA_OK(e, cudaMalloc(&t->stem_wb, sizeof(__nv_bfloat16) * TW_C * TW_STEM_K));
     k_stem_weights<<<(TW_C * TW_STEM_K + 255) / 256, 256, 0, S_(stream)>>>(t->stem_w, t->stem_wb);
     SGO_CUDA_OK(e, cudaGetLastError());
+    SGO_CUDA_OK(e, cudaMalloc(&t->head_w4, sizeof(float) * TW_C * 4));
+    SGO_CUDA_OK(e, cudaMalloc(&t->head_b4, sizeof(float) * 4));
+    SGO_CUDA_OK(e, cudaMalloc(&t->feat, sizeof(float) * 4 * (size_t)P * max_positions));
+    k_head_w4<<<1, TW_C, 0, S_(stream)>>>(t->pol_conv_w, t->pol_conv_b, t->val_conv_w, t->val_conv_b, t->head_w4, t->head_b4);
+    SGO_CUDA_OK(e, cudaGetLastError());
+    SGO_CUDA_OK(e, cudaFuncSetAttribute(k_heads_fc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(float) * (4 * P * FC_PB + FC_PB * A + FC_PB * (FC_THREADS / 32))));
     SGO_CUDA_OK(e, cudaMalloc(&t->err, sizeof(int32_t)));
     SGO_CUDA_OK(e, cudaMemsetAsync(t->err, 0, sizeof(int32_t), S_(stream)));
     int dev = 0;
@@ -752,7 +888,7 @@ extern "C" int sgo_tower_load_weights(sgo_engine *e, int32_t slot, const sgo_tow
 
 static int g_conv_variant = 0;
 
-static int launch_conv(sgo_engine *e, sgo_tower *t, int n, int layer, int in, int out, int skip, void *stream)
+static int launch_conv(sgo_engine *e, sgo_tower *t, int n, int layer, int in, int out, int skip, void *stream, bool heads = false)
 {
     ConvArgs a;
     a.variant = g_conv_variant;
@@ -770,6 +906,8 @@ static int launch_conv(sgo_engine *e, sgo_tower *t, int n, int layer, int in, in
         pa.W = a.W; pa.RT = a.RT; pa.rows_per_pos = a.rows_per_pos; pa.YB = a.YB; pa.n_tiles = a.n_tiles; pa.w_row0 = a.w_row0;
         pa.n_taps = 9; pa.kchunks = TW_C / TW_KCH;
         pa.relu = 1; pa.f0 = t->f0; pa.p0 = t->p0; pa.f1 = t->f1; pa.bias = a.bias; pa.skip = a.skip; pa.out = a.out; pa.err = a.err;
+        pa.head_w4 = heads ? t->head_w4 : nullptr; pa.head_b4 = t->head_b4; pa.feat = t->feat;
+        if (heads) pa.out = nullptr;               // the last layer's activations are consumed by the fused 1x1 head convs only
         int pairs = t->sm_count / 2;
         if (pairs > a.n_tiles) pairs = a.n_tiles;
         k_conv3x3_pair<<<2 * pairs, TW_THREADS, PR_SMEM_BYTES, S_(stream)>>>(t->pmaps[in], pa);
@@ -807,6 +945,7 @@ extern "C" int sgo_tower_forward(sgo_engine *e, int32_t slot, int32_t which, con
         pa.W = t->W; pa.RT = t->RT; pa.rows_per_pos = t->W + 1; pa.YB = n * (t->W + 1) + 1;
         pa.n_tiles = (pa.YB + t->RT - 1) / t->RT; pa.w_row0 = 0; pa.relu = 1; pa.n_taps = 1; pa.kchunks = TW_STEM_K / TW_KCH;
         pa.f0 = t->f0; pa.p0 = t->p0; pa.f1 = t->f1; pa.bias = t->stem_b; pa.skip = nullptr; pa.out = t->act[0]; pa.err = t->err;
+        pa.head_w4 = t->n_blocks == 0 ? t->head_w4 : nullptr; pa.head_b4 = t->head_b4; pa.feat = t->feat;
         int pairs = t->sm_count / 2;
         if (pairs > pa.n_tiles) pairs = pa.n_tiles;
         k_conv3x3_pair<<<2 * pairs, TW_THREADS, PR_SMEM_BYTES, S_(stream)>>>(t->pmaps[3], pa);
@@ -821,7 +960,7 @@ extern "C" int sgo_tower_forward(sgo_engine *e, int32_t slot, int32_t which, con
         int tmp = (x + 1) % 3, y = (x + 2) % 3;
         int rc = launch_conv(e, t, n, 2 * b, x, tmp, -1, stream);           // conv1 + BN + ReLU   (model.py:39-41)
         if (rc) return rc;
-        rc = launch_conv(e, t, n, 2 * b + 1, tmp, y, x, stream);            // conv2 + BN + skip + ReLU (model.py:42-45)
+        rc = launch_conv(e, t, n, 2 * b + 1, tmp, y, x, stream, t->use_pair && b == t->n_blocks - 1);   // conv2 + BN + skip + ReLU (model.py:42-45)
         if (rc) return rc;
         x = y;
     }
@@ -831,11 +970,23 @@ extern "C" int sgo_tower_forward(sgo_engine *e, int32_t slot, int32_t which, con
     h.pcw = t->pol_conv_w; h.pcb = t->pol_conv_b; h.pfw = t->pol_fc_w; h.pfb = t->pol_fc_b;
     h.vcw = t->val_conv_w; h.vcb = t->val_conv_b; h.v1w = t->val_fc1_w; h.v1b = t->val_fc1_b;
     h.v2w = t->val_fc2_w; h.v2b = t->val_fc2_b; h.policy = d_policy; h.value = d_value;
-    int hs = (HD_P * (4 * P + e->A + 256) + TW_C * 4) * (int)sizeof(float);
-    int hgrid = (n + HD_P - 1) / HD_P;
-    if (hgrid > 4 * t->sm_count) hgrid = 4 * t->sm_count;
-    k_heads<<<hgrid, HD_THREADS, hs, S_(stream)>>>(h);
-    SGO_LAUNCHED(e);
+    if (t->use_pair) {
+        FcArgs f;
+        f.n = n; f.S = t->S; f.W = t->W; f.scatter = scatter; f.index = d_index; f.syms = d_sym; f.feat = t->feat;
+        f.pfw = t->pol_fc_w; f.pfb = t->pol_fc_b; f.v1w = t->val_fc1_w; f.v1b = t->val_fc1_b; f.v2w = t->val_fc2_w; f.v2b = t->val_fc2_b;
+        f.policy = d_policy; f.value = d_value;
+        int fs = (int)sizeof(float) * (4 * P * FC_PB + FC_PB * e->A + FC_PB * (FC_THREADS / 32));
+        int fgrid = (n + FC_PB - 1) / FC_PB;
+        if (fgrid > 2 * t->sm_count) fgrid = 2 * t->sm_count;
+        k_heads_fc<<<fgrid, FC_THREADS, fs, S_(stream)>>>(f);
+        SGO_LAUNCHED(e);
+    } else {
+        int hs = (HD_P * (4 * P + e->A + 256) + TW_C * 4) * (int)sizeof(float);
+        int hgrid = (n + HD_P - 1) / HD_P;
+        if (hgrid > 4 * t->sm_count) hgrid = 4 * t->sm_count;
+        k_heads<<<hgrid, HD_THREADS, hs, S_(stream)>>>(h);
+        SGO_LAUNCHED(e);
+    }
     if (prof) { cudaEventRecord(pe[3], S_(stream)); t->prof_pos[t->prof_n++] = n; }
     return 0;
 }
