@@ -265,6 +265,7 @@ def run_ours(a):
     records = sd.pack_records(bg.finish())
     gathered = sd.gather_records(records.to(dev) if world > 1 else records, dst=0, device=dev if world > 1 else None)
     if rank != 0:
+        torch.distributed.destroy_process_group()
         return
     peaks = measured_peaks()
     conv_flops = prof['positions'] * FLOP_PER_CONV_POS * 2 * a.blocks
@@ -291,7 +292,7 @@ def run_ours(a):
                  d2h_bytes_per_step=r2['d2h'] / a.steps, moves_per_sec=r2['plies'] / (r2['ms'] * 1e-3)),
         gpu_launches=r['launches'],
         clocks=clocks,
-        roofline=dict(bound="tensor", kernel="k_conv3x3_tc", achieved=achieved, peak=peaks['tflops'], unit="TFLOP/s",
+        roofline=dict(bound="tensor", kernel="k_conv3x3_pair", achieved=achieved, peak=peaks['tflops'], unit="TFLOP/s",
                       frac=achieved / peaks['tflops'], traffic=traffic, peak_source=peaks['src'],
                       launches=prof['conv_launches'], avg_launch_ms=prof['conv_ms'] / max(1, prof['conv_launches']),
                       share_of_step=prof['conv_ms'] / r['ms'], stem_ms=prof['stem_ms'], heads_ms=prof['heads_ms']),
@@ -299,6 +300,8 @@ def run_ours(a):
     if world == 1 and not a.no_cpu:
         out["cpu_baseline"], _ = _cpu_baseline_dict(a.mode, a.blocks, 1, 2)
     print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 def main():

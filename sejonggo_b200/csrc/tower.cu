@@ -1,22 +1,22 @@
 // tower.cu — the residual policy/value tower of model.py:55-96 on sm_100a.
 //
-//   stem   Conv3x3 "valid" 17->C on the SxS input planes + BN + ReLU (model.py:57-61).
-//          Computed straight from the packed bitboards: input-plane construction
-//          (play.py:295-299) and the symmetry gather (symmetry.py:45-114) are fused in;
-//          no [S,S,17] plane tensor ever touches HBM on this path.
-//   tower  2*N_RESIDUAL_BLOCKS Conv3x3 "same" C->C (+BN folded, +skip, ReLU) as
-//          implicit GEMMs on the 5th-gen tensor cores: TMA (cp.async.bulk.tensor, 128B
-//          swizzle) stages a [RT x W pixels, 64 ch] activation box per filter tap and a
-//          [C x 64] weight box per tap into shared memory, one thread issues
-//          tcgen05.mma (M=128,N=256,K=16, bf16 -> fp32 in TMEM), the epilogue warps read
-//          the accumulators back with tcgen05.ld and fuse bias/skip/ReLU/bf16.
-//   heads  1x1 convs + dense policy (softmax) / value (tanh) heads (model.py:72-92),
-//          fp32, with the "reverse" symmetry policy gather fused into the store.
+//   stem   Conv3x3 "valid" 17->C on the SxS input planes + BN + ReLU (model.py:57-61) as
+//          im2col straight from the packed bitboards (input-plane construction play.py:295-299
+//          and the symmetry gather symmetry.py:45-114 fused in; values 0/1/+-1 are exact in
+//          bf16) followed by ONE tensor-core GEMM (K = 153 -> 192) through the pair kernel.
+//   tower  2*N_RESIDUAL_BLOCKS Conv3x3 "same" C->C (+BN folded, +skip, ReLU): implicit GEMMs on
+//          CTA pairs — TMA boxes per filter tap, tcgen05.mma.cta_group::2, double-buffered TMEM
+//          accumulators (conv_pair.cuh).
+//   heads  the two 1x1 convs are fused into the last conv's epilogue (its activations never
+//          reach HBM); k_heads_fc does the dense policy (softmax) / value (tanh) layers
+//          (model.py:72-92) in fp32 with the "reverse" symmetry policy gather fused in.
 //
-// Activation layout in HBM: bf16 [YB][W][C], W = S-2, YB = n_pos*(W+1)+1: every position
+// Activation layout in HBM: bf16 [YB][W][C], W = S-2 (Q11), YB = n_pos*(W+1)+1: every position
 // owns W pixel rows preceded by ONE all-zero pad row (shared top/bottom halo); left/right
 // halos come from TMA out-of-bounds zero fill.  A conv tile = RT consecutive rows (RT*W<=256),
-// so its 9 shifted A operands are plain 3-D TMA boxes at (c0, dx, yb0+dy).
+// so its 9 shifted A operands are plain 3-D TMA boxes at (c0, dx, yb0+dy).  (A dense 4-D
+// layout without pad rows was tried and is slower: more TMA boxes per k-block — see
+// profiles/r01_experiment_dense_*.json.)
 #include "engine.h"
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -26,8 +26,6 @@
 
 #define TW_C 256
 #define TW_KCH 64
-#define TW_STAGES 3
-#define TW_TILE_BYTES (256 * 128)
 #define TW_THREADS 192
 #define TW_SPIN_LIMIT (1u << 21)
 #define TW_STEM_K 192                      // 9 taps x 17 planes = 153, padded to 3 x 64
@@ -41,13 +39,11 @@ struct sgo_tower {
     float *pol_conv_w, *pol_conv_b, *pol_fc_w, *pol_fc_b;
     float *val_conv_w, *val_conv_b, *val_fc1_w, *val_fc1_b, *val_fc2_w, *val_fc2_b;
     __nv_bfloat16 *act[3];                  // [YB][W][C]
-    CUtensorMap map_act[3];
-    CUtensorMap map_w;
     struct PairMaps *pmaps;                 // [3] tensor maps of the CTA-pair kernel (conv_pair.cuh); [3] = stem im2col
     __nv_bfloat16 *stem_col;                // [YB][W][TW_STEM_K] im2col of the input planes (0/1, +-1)
     __nv_bfloat16 *stem_wb;                 // [C co][TW_STEM_K] bf16 stem weights, k = tap*17 + plane
     float *head_w4, *head_b4, *feat;        // fused 1x1 head convs: [C][4], [4]; features [max_pos][W*W][4]
-    int f0, p0, f1, use_pair;
+    int f0, p0, f1;
     int32_t *err;
     int sm_count;
     // optional live profiling (bench.py roofline): 4 events per forward call
@@ -132,171 +128,6 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
 {
     return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), K-major both, N>>3 at 17, M>>4 at 24
-#define TW_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24))
-
-struct ConvArgs {
-    int W, RT, rows_per_pos, YB, n_tiles, w_row0, relu;
-    int variant;              // profiling experiments only: 1 = skip B loads, 2 = skip A loads, 4 = skip epilogue global traffic
-    const float *bias;
-    const __nv_bfloat16 *skip;
-    __nv_bfloat16 *out;
-    int32_t *err;
-};
-
-struct ConvSmemTail {
-    uint64_t full[TW_STAGES], empty[TW_STAGES], tmem_full, tmem_empty;
-    uint32_t tmem_base;
-    uint32_t pad;
-    float bias[TW_C];
-};
-#define TW_SMEM_BYTES (TW_STAGES * 2 * TW_TILE_BYTES + (int)sizeof(ConvSmemTail) + 1024)
-
-// One persistent CTA per SM.  warp 0: TMA producer, warp 1: MMA issuer + TMEM owner,
-// warps 2-5: epilogue (warp w reads TMEM lanes 32*(w%4) .. +31).
-__global__ void __launch_bounds__(TW_THREADS, 1)
-k_conv3x3_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w, ConvArgs a)
-{
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    ConvSmemTail *tail = reinterpret_cast<ConvSmemTail *>(smem + TW_STAGES * 2 * TW_TILE_BYTES);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_in) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_w) : "memory");
-        for (int s = 0; s < TW_STAGES; s++) { mbar_init(&tail->full[s], 1); mbar_init(&tail->empty[s], 1); }
-        mbar_init(&tail->tmem_full, 1);
-        mbar_init(&tail->tmem_empty, 128);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tail->tmem_base)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    for (int i = threadIdx.x; i < TW_C; i += blockDim.x) tail->bias[i] = a.bias[i];
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tail->tmem_base;
-    const uint32_t a_box_bytes = (uint32_t)(TW_KCH * 2 * a.W * a.RT);
-
-    if (warp == 0) {
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            bool ok = true;
-            for (int tile = blockIdx.x; tile < a.n_tiles && ok; tile += gridDim.x) {
-                int yb0 = tile * a.RT;
-                for (int tap = 0; tap < 9 && ok; tap++) {
-                    int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                    for (int kc = 0; kc < TW_C / TW_KCH; kc++) {
-                        ok = mbar_wait(&tail->empty[stage], phase ^ 1, a.err);
-                        if (!ok) break;
-                        uint8_t *sa = smem + (size_t)stage * 2 * TW_TILE_BYTES, *sb = sa + TW_TILE_BYTES;
-                        if (a.variant & 3) {          // experiments: drop one or both operand loads
-                            uint32_t bytes = ((a.variant & 2) ? 0u : a_box_bytes) + ((a.variant & 1) ? 0u : (uint32_t)TW_TILE_BYTES);
-                            if (bytes) mbar_expect_tx(&tail->full[stage], bytes); else mbar_arrive(&tail->full[stage]);
-                            if (!(a.variant & 2)) tma_load_3d(sa, &map_in, kc * TW_KCH, dx, yb0 + dy, &tail->full[stage]);
-                            if (!(a.variant & 1)) tma_load_2d(sb, &map_w, kc * TW_KCH, a.w_row0 + tap * TW_C, &tail->full[stage]);
-                            if (++stage == TW_STAGES) { stage = 0; phase ^= 1; }
-                            continue;
-                        }
-                        mbar_expect_tx(&tail->full[stage], a_box_bytes + TW_TILE_BYTES);
-                        tma_load_3d(sa, &map_in, kc * TW_KCH, dx, yb0 + dy, &tail->full[stage]);
-                        tma_load_2d(sb, &map_w, kc * TW_KCH, a.w_row0 + tap * TW_C, &tail->full[stage]);
-                        if (++stage == TW_STAGES) { stage = 0; phase ^= 1; }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0, tphase = 0;
-            bool ok = true;
-            for (int tile = blockIdx.x; tile < a.n_tiles && ok; tile += gridDim.x) {
-                ok = mbar_wait(&tail->tmem_empty, tphase ^ 1, a.err);      // epilogue drained the accumulators
-                if (!ok) break;
-                tc_fence_after();
-                for (int kb = 0; kb < 9 * (TW_C / TW_KCH); kb++) {
-                    ok = mbar_wait(&tail->full[stage], phase, a.err);
-                    if (!ok) break;
-                    tc_fence_after();
-                    uint32_t sa = smem_u32(smem + (size_t)stage * 2 * TW_TILE_BYTES), sb = sa + TW_TILE_BYTES;
-#pragma unroll
-                    for (int h = 0; h < 2; h++)
-#pragma unroll
-                        for (int k = 0; k < TW_KCH / 16; k++)
-                            umma_bf16(tmem_base + h * 256, umma_desc_sw128(sa + h * (128 * 128) + k * 32),
-                                      umma_desc_sw128(sb + k * 32), TW_IDESC, (kb | k) ? 1u : 0u);
-                    umma_commit(&tail->empty[stage]);                       // frees the smem slot when the MMAs retire
-                    if (++stage == TW_STAGES) { stage = 0; phase ^= 1; }
-                }
-                umma_commit(&tail->tmem_full);
-                tphase ^= 1;
-            }
-        }
-    } else {
-        const int q = warp & 3;
-        const int rr = q * 32 + lane;
-        uint32_t tphase = 0;
-        bool ok = true;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-            if (ok) ok = mbar_wait(&tail->tmem_full, tphase, a.err);
-            ok = __all_sync(SGO_FULL, ok);
-            if (!ok) break;
-            tc_fence_after();
-            int yb0 = tile * a.RT;
-#pragma unroll 1
-            for (int h = 0; h < 2; h++) {
-                int r = h * 128 + rr;
-                int ry = r / a.W, x = r - ry * a.W, yb = yb0 + ry;
-                bool valid = r < a.RT * a.W && yb < a.YB && (yb % a.rows_per_pos) != 0;
-                size_t gofs = ((size_t)yb * a.W + x) * TW_C;
-#pragma unroll 1
-                for (int c = 0; c < TW_C / 32; c++) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + h * 256 + c * 32, v);
-                    if (valid && !(a.variant & 4)) {
-                        uint4 sk[4];
-                        if (a.skip) {
-                            const uint4 *sp = reinterpret_cast<const uint4 *>(a.skip + gofs + c * 32);
-#pragma unroll
-                            for (int j = 0; j < 4; j++) sk[j] = sp[j];
-                        }
-                        uint4 o[4];
-                        uint32_t *ow = reinterpret_cast<uint32_t *>(o);
-                        const uint32_t *sw = reinterpret_cast<const uint32_t *>(sk);
-#pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            float f0 = __uint_as_float(v[2 * j]) + tail->bias[c * 32 + 2 * j];
-                            float f1 = __uint_as_float(v[2 * j + 1]) + tail->bias[c * 32 + 2 * j + 1];
-                            if (a.skip) {
-                                __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162 *>(&sw[j]);
-                                f0 += __bfloat162float(s2.x);
-                                f1 += __bfloat162float(s2.y);
-                            }
-                            if (a.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
-                            __nv_bfloat162 p = __floats2bfloat162_rn(f0, f1);
-                            ow[j] = *reinterpret_cast<uint32_t *>(&p);
-                        }
-                        uint4 *op = reinterpret_cast<uint4 *>(a.out + gofs + c * 32);
-#pragma unroll
-                        for (int j = 0; j < 4; j++) op[j] = o[j];
-                    }
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(&tail->tmem_empty);
-            tphase ^= 1;
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
-    }
-}
-
 #include "conv_pair.cuh"
 
 // ------------------------------------------------------------------ stem
@@ -312,62 +143,6 @@ __device__ __forceinline__ void sym_src_t(int S, int sym, int y, int x, int &sy,
     case 5: sy = m - y; sx = m - x; break;
     case 6: sy = m - x; sx = y; break;
     default: sy = m - x; sx = m - y; break;
-    }
-}
-
-// grid-stride over positions, 256 threads = output channels.  Weights (9*17*C fp32) live in
-// shared memory for the CTA's lifetime; each cell's 16 stone planes are one 16-bit mask.
-__global__ void __launch_bounds__(TW_C, 1)
-k_stem(const Board *boards, const int32_t *index, const int32_t *syms, int n, int S, const float *w, const float *b,
-       __nv_bfloat16 *out)
-{
-    extern __shared__ float sw[];                        // [9][16][C] stone-plane weights
-    __shared__ uint16_t cell[SGO_MAXS * SGO_MAXS];
-    __shared__ int s_tm;
-    const int co = threadIdx.x, W = S - 2;
-    float wtm = 0.f;
-    for (int tap = 0; tap < 9; tap++) {
-        for (int p = 0; p < 16; p++) sw[(tap * 16 + p) * TW_C + co] = w[(tap * 17 + p) * TW_C + co];
-        wtm += w[(tap * 17 + 16) * TW_C + co];            // plane 16 is constant +-1 over the valid window
-    }
-    const float bias = b[co];
-    __syncthreads();
-    for (int i = blockIdx.x; i < n; i += gridDim.x) {
-        const Board *bd = boards + (index ? index[i] : i);
-        const int sym = syms ? (syms[i] & 7) : 0;
-        const int tm = bd->to_move, head = bd->head;
-        for (int c = threadIdx.x; c < S * S; c += blockDim.x) {
-            int y = c / S, x = c - y * S, sy, sx;
-            sym_src_t(S, sym, y, x, sy, sx);
-            uint32_t m = 0;
-#pragma unroll
-            for (int k = 0; k < SGO_HIST; k++) {
-                int slot = (head + SGO_HIST - k) & (SGO_HIST - 1);
-                uint32_t bl = (bd->st[slot][0][sy] >> sx) & 1u, wh = (bd->st[slot][1][sy] >> sx) & 1u;
-                uint32_t own = tm == 1 ? bl : wh, opp = tm == 1 ? wh : bl;
-                m |= (own << (2 * k)) | (opp << (2 * k + 1));
-            }
-            cell[c] = (uint16_t)m;
-        }
-        if (threadIdx.x == 0) s_tm = tm;
-        __syncthreads();
-        const float base = bias + (float)s_tm * wtm;
-        const size_t row0 = (size_t)i * (W + 1) + 1;
-        for (int y = 0; y < W; y++)
-            for (int x = 0; x < W; x++) {
-                float acc = base;
-#pragma unroll
-                for (int tap = 0; tap < 9; tap++) {
-                    uint32_t m = cell[(y + tap / 3) * S + x + tap % 3];
-                    while (m) {
-                        int p = __ffs(m) - 1;
-                        m &= m - 1;
-                        acc += sw[(tap * 16 + p) * TW_C + co];
-                    }
-                }
-                out[((row0 + y) * W + x) * TW_C + co] = __float2bfloat16(fmaxf(acc, 0.f));
-            }
-        __syncthreads();
     }
 }
 
@@ -447,135 +222,6 @@ __global__ void k_stem_weights(const float *w, __nv_bfloat16 *wb)
 }
 
 // ------------------------------------------------------------------ heads
-#define HD_P 4                      // positions per CTA pass (dense weights are read once per pass)
-#define HD_THREADS 256
-
-__device__ __forceinline__ float block_reduce(float v, bool is_max, float *scratch)
-{
-    for (int o = 16; o; o >>= 1) {
-        float t = __shfl_xor_sync(SGO_FULL, v, o);
-        v = is_max ? fmaxf(v, t) : v + t;
-    }
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float r = scratch[0];
-    for (int i = 1; i < HD_THREADS / 32; i++) r = is_max ? fmaxf(r, scratch[i]) : r + scratch[i];
-    return r;
-}
-
-struct HeadArgs {
-    int n, S, W, scatter;
-    const int32_t *index, *syms;
-    const __nv_bfloat16 *act;
-    const float *pcw, *pcb, *pfw, *pfb, *vcw, *vcb, *v1w, *v1b, *v2w, *v2b;
-    float *policy, *value;
-};
-
-__global__ void __launch_bounds__(HD_THREADS)
-k_heads(HeadArgs h)
-{
-    extern __shared__ float hs[];
-    const int W = h.W, P = W * W, F = 2 * P, A = h.S * h.S + 1;
-    float *featp = hs;                          // [HD_P][F]
-    float *featv = featp + HD_P * F;            // [HD_P][F]
-    float *logit = featv + HD_P * F;            // [HD_P][A]
-    float *hid = logit + HD_P * A;              // [HD_P][256]
-    float *w4 = hid + HD_P * 256;               // [C][4] 1x1 conv weights (p0,p1,v0,v1)
-    __shared__ float scratch[HD_THREADS / 32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int c = threadIdx.x; c < TW_C; c += blockDim.x) {
-        w4[c * 4 + 0] = h.pcw[c * 2]; w4[c * 4 + 1] = h.pcw[c * 2 + 1];
-        w4[c * 4 + 2] = h.vcw[c * 2]; w4[c * 4 + 3] = h.vcw[c * 2 + 1];
-    }
-    __syncthreads();
-    for (int base = blockIdx.x * HD_P; base < h.n; base += gridDim.x * HD_P) {
-        int np = min(HD_P, h.n - base);
-        // 1x1 convs + BN(folded) + ReLU: one warp per pixel, lanes split the 256 channels
-        for (int t = warp; t < np * P; t += HD_THREADS / 32) {
-            int pi = t / P, pix = t - pi * P, y = pix / W, x = pix - y * W;
-            size_t row = (size_t)(base + pi) * (W + 1) + 1 + y;
-            const uint4 *ap = reinterpret_cast<const uint4 *>(h.act + (row * W + x) * TW_C) + lane;
-            uint4 raw = *ap;
-            const __nv_bfloat162 *a2 = reinterpret_cast<const __nv_bfloat162 *>(&raw);
-            float s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                float f0 = __bfloat162float(a2[j].x), f1 = __bfloat162float(a2[j].y);
-                const float *wa = w4 + (lane * 8 + 2 * j) * 4;
-                s0 = fmaf(f0, wa[0], s0); s1 = fmaf(f0, wa[1], s1); s2 = fmaf(f0, wa[2], s2); s3 = fmaf(f0, wa[3], s3);
-                s0 = fmaf(f1, wa[4], s0); s1 = fmaf(f1, wa[5], s1); s2 = fmaf(f1, wa[6], s2); s3 = fmaf(f1, wa[7], s3);
-            }
-            for (int o = 16; o; o >>= 1) {
-                s0 += __shfl_xor_sync(SGO_FULL, s0, o); s1 += __shfl_xor_sync(SGO_FULL, s1, o);
-                s2 += __shfl_xor_sync(SGO_FULL, s2, o); s3 += __shfl_xor_sync(SGO_FULL, s3, o);
-            }
-            if (lane == 0) {
-                featp[pi * F + pix * 2 + 0] = fmaxf(s0 + h.pcb[0], 0.f);      // flatten order HWC (model.py:77-79)
-                featp[pi * F + pix * 2 + 1] = fmaxf(s1 + h.pcb[1], 0.f);
-                featv[pi * F + pix * 2 + 0] = fmaxf(s2 + h.vcb[0], 0.f);
-                featv[pi * F + pix * 2 + 1] = fmaxf(s3 + h.vcb[1], 0.f);
-            }
-        }
-        __syncthreads();
-        // policy dense F -> A (thread per action), value dense F -> 256 (thread per unit)
-        for (int a0 = threadIdx.x; a0 < A; a0 += blockDim.x) {
-            float acc[HD_P];
-#pragma unroll
-            for (int p = 0; p < HD_P; p++) acc[p] = h.pfb[a0];
-            for (int i = 0; i < F; i++) {
-                float wv = h.pfw[(size_t)i * A + a0];
-#pragma unroll
-                for (int p = 0; p < HD_P; p++) acc[p] = fmaf(featp[p * F + i], wv, acc[p]);
-            }
-#pragma unroll
-            for (int p = 0; p < HD_P; p++) logit[p * A + a0] = acc[p];
-        }
-        {
-            int j = threadIdx.x;
-            float acc[HD_P];
-#pragma unroll
-            for (int p = 0; p < HD_P; p++) acc[p] = h.v1b[j];
-            for (int i = 0; i < F; i++) {
-                float wv = h.v1w[(size_t)i * 256 + j];
-#pragma unroll
-                for (int p = 0; p < HD_P; p++) acc[p] = fmaf(featv[p * F + i], wv, acc[p]);
-            }
-#pragma unroll
-            for (int p = 0; p < HD_P; p++) hid[p * 256 + j] = fmaxf(acc[p], 0.f) * h.v2w[j];
-        }
-        __syncthreads();
-        for (int p = 0; p < np; p++) {
-            float mx = -3.4e38f;
-            for (int a0 = threadIdx.x; a0 < A; a0 += blockDim.x) mx = fmaxf(mx, logit[p * A + a0]);
-            mx = block_reduce(mx, true, scratch);
-            float sum = 0.f;
-            for (int a0 = threadIdx.x; a0 < A; a0 += blockDim.x) {
-                float e = expf(logit[p * A + a0] - mx);
-                logit[p * A + a0] = e;
-                sum += e;
-            }
-            sum = block_reduce(sum, false, scratch);
-            float vs = block_reduce(hid[p * 256 + threadIdx.x], false, scratch);
-            int i = base + p;
-            size_t orow = h.scatter ? (size_t)(h.index ? h.index[i] : i) : (size_t)i;
-            int sym = h.syms ? (h.syms[i] & 7) : 0;
-            float inv = 1.f / sum;
-            for (int a0 = threadIdx.x; a0 < A; a0 += blockDim.x) {
-                int src = a0;
-                if (a0 < h.S * h.S) {                       // "reverse" gather re-uses the forward map (Q8)
-                    int y = a0 / h.S, x = a0 - y * h.S, sy, sx;
-                    sym_src_t(h.S, sym, y, x, sy, sx);
-                    src = sy * h.S + sx;
-                }
-                h.policy[orow * A + a0] = logit[p * A + src] * inv;
-            }
-            if (threadIdx.x == 0) h.value[orow] = tanhf(vs + h.v2b[0]);
-        }
-        __syncthreads();
-    }
-}
-
 // Dense heads on the fused 1x1-conv features (feat[pos][pix][p0,p1,v0,v1], fp32, post BN+ReLU):
 // policy Dense(2P -> A) + softmax, value Dense(2P -> 256) + ReLU + Dense(256 -> 1) + tanh
 // (model.py:77-92).  A CTA owns FC_PB positions per pass: features sit transposed in shared
@@ -714,23 +360,9 @@ static int make_maps(sgo_engine *e, sgo_tower *t)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return sgo_fail(e, "cuTensorMapEncodeTiled unavailable");
-    for (int i = 0; i < 3; i++) {
-        cuuint64_t dims[3] = {(cuuint64_t)TW_C, (cuuint64_t)t->W, (cuuint64_t)t->YB};
-        cuuint64_t strides[2] = {(cuuint64_t)TW_C * 2, (cuuint64_t)TW_C * 2 * t->W};
-        cuuint32_t box[3] = {TW_KCH, (cuuint32_t)t->W, (cuuint32_t)t->RT};
-        cuuint32_t es[3] = {1, 1, 1};
-        CUresult r = enc(&t->map_act[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, t->act[i], dims, strides, box, es,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(activations) failed");
-    }
-    cuuint64_t dims[2] = {(cuuint64_t)TW_C, (cuuint64_t)t->n_layers * 9 * TW_C};
+    cuuint64_t dims[2] = {(cuuint64_t)TW_C, (cuuint64_t)(t->n_layers ? t->n_layers : 1) * 9 * TW_C};
     cuuint64_t strides[1] = {(cuuint64_t)TW_C * 2};
-    cuuint32_t box[2] = {TW_KCH, TW_C};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&t->map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, t->conv_w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(weights) failed");
     // CTA-pair kernel: rank 0 = f0 full rows + p0 pixels, rank 1 = (W-p0) pixels + f1 full rows
     t->f0 = 128 / t->W;
     t->p0 = 128 - t->f0 * t->W;
@@ -871,51 +503,34 @@ extern "C" int sgo_tower_load_weights(sgo_engine *e, int32_t slot, const sgo_tow
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev);
-    SGO_CUDA_OK(e, cudaFuncSetAttribute(k_conv3x3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM_BYTES));
     SGO_CUDA_OK(e, cudaFuncSetAttribute(k_conv3x3_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM_BYTES));
-    {
-        const char *v = getenv("SGO_CONV_SINGLE");            // debugging switch: force the single-CTA kernel
-        t->use_pair = !(v && v[0] == '1');
-    }
-    SGO_CUDA_OK(e, cudaFuncSetAttribute(k_stem, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 16 * TW_C * (int)sizeof(float)));
-    int hs = (HD_P * (4 * P + A + 256) + TW_C * 4) * (int)sizeof(float);
-    SGO_CUDA_OK(e, cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, hs));
     int rc = make_maps(e, t);
     if (rc) return rc;
     SGO_CUDA_OK(e, cudaStreamSynchronize(S_(stream)));
     return 0;
 }
 
-static int g_conv_variant = 0;
-
+// one launch of the pair kernel: a tower conv layer (layer >= 0) or the stem GEMM (layer < 0)
 static int launch_conv(sgo_engine *e, sgo_tower *t, int n, int layer, int in, int out, int skip, void *stream, bool heads = false)
 {
-    ConvArgs a;
-    a.variant = g_conv_variant;
-    a.W = t->W; a.RT = t->RT; a.rows_per_pos = t->W + 1;
-    a.YB = n * (t->W + 1) + 1;
-    a.n_tiles = (a.YB + t->RT - 1) / t->RT;
-    a.w_row0 = layer * 9 * TW_C;
-    a.relu = 1;
-    a.bias = t->conv_b + (size_t)layer * TW_C;
-    a.skip = skip >= 0 ? t->act[skip] : nullptr;
-    a.out = t->act[out];
-    a.err = t->err;
-    if (t->use_pair && !g_conv_variant) {
-        PairArgs pa;
-        pa.W = a.W; pa.RT = a.RT; pa.rows_per_pos = a.rows_per_pos; pa.YB = a.YB; pa.n_tiles = a.n_tiles; pa.w_row0 = a.w_row0;
-        pa.n_taps = 9; pa.kchunks = TW_C / TW_KCH;
-        pa.relu = 1; pa.f0 = t->f0; pa.p0 = t->p0; pa.f1 = t->f1; pa.bias = a.bias; pa.skip = a.skip; pa.out = a.out; pa.err = a.err;
-        pa.head_w4 = heads ? t->head_w4 : nullptr; pa.head_b4 = t->head_b4; pa.feat = t->feat;
-        if (heads) pa.out = nullptr;               // the last layer's activations are consumed by the fused 1x1 head convs only
-        int pairs = t->sm_count / 2;
-        if (pairs > a.n_tiles) pairs = a.n_tiles;
-        k_conv3x3_pair<<<2 * pairs, TW_THREADS, PR_SMEM_BYTES, S_(stream)>>>(t->pmaps[in], pa);
-        SGO_LAUNCHED(e);
-        return 0;
+    PairArgs pa;
+    pa.W = t->W; pa.RT = t->RT; pa.rows_per_pos = t->W + 1;
+    pa.YB = n * (t->W + 1) + 1;
+    pa.n_tiles = (pa.YB + t->RT - 1) / t->RT;
+    pa.relu = 1; pa.f0 = t->f0; pa.p0 = t->p0; pa.f1 = t->f1; pa.err = t->err;
+    if (layer >= 0) {
+        pa.n_taps = 9; pa.kchunks = TW_C / TW_KCH; pa.w_row0 = layer * 9 * TW_C;
+        pa.bias = t->conv_b + (size_t)layer * TW_C;
+    } else {
+        pa.n_taps = 1; pa.kchunks = TW_STEM_K / TW_KCH; pa.w_row0 = 0;
+        pa.bias = t->stem_b;
     }
-    int grid = a.n_tiles < t->sm_count ? a.n_tiles : t->sm_count;
-    k_conv3x3_tc<<<grid, TW_THREADS, TW_SMEM_BYTES, S_(stream)>>>(t->map_act[in], t->map_w, a);
+    pa.skip = skip >= 0 ? t->act[skip] : nullptr;
+    pa.out = heads ? nullptr : t->act[out];      // the last layer's activations are consumed by the fused 1x1 head convs only
+    pa.head_w4 = heads ? t->head_w4 : nullptr; pa.head_b4 = t->head_b4; pa.feat = t->feat;
+    int pairs = t->sm_count / 2;
+    if (pairs > pa.n_tiles) pairs = pa.n_tiles;
+    k_conv3x3_pair<<<2 * pairs, TW_THREADS, PR_SMEM_BYTES, S_(stream)>>>(t->pmaps[layer >= 0 ? in : 3], pa);
     SGO_LAUNCHED(e);
     return 0;
 }
@@ -932,27 +547,16 @@ extern "C" int sgo_tower_forward(sgo_engine *e, int32_t slot, int32_t which, con
     if (n == 0) return 0;
     const Board *boards = which ? e->leaf_boards : e->boards;
     int P = t->W * t->W;
-    int grid = n < t->sm_count ? n : t->sm_count;
     const bool prof = t->prof_on && t->prof_n < TW_PROF_MAX;
     cudaEvent_t *pe = prof ? t->prof_ev + (size_t)t->prof_n * 4 : nullptr;
     if (prof) cudaEventRecord(pe[0], S_(stream));
-    if (t->use_pair) {
-        // stem = im2col from the bitboards + one pair-kernel GEMM (K = 192) with the bias/ReLU epilogue
-        int g2 = n < 8 * t->sm_count ? n : 8 * t->sm_count;
-        k_stem_im2col<<<g2, 256, 0, S_(stream)>>>(boards, d_index, d_sym, n, t->S, t->stem_col);
-        SGO_LAUNCHED(e);
-        PairArgs pa;
-        pa.W = t->W; pa.RT = t->RT; pa.rows_per_pos = t->W + 1; pa.YB = n * (t->W + 1) + 1;
-        pa.n_tiles = (pa.YB + t->RT - 1) / t->RT; pa.w_row0 = 0; pa.relu = 1; pa.n_taps = 1; pa.kchunks = TW_STEM_K / TW_KCH;
-        pa.f0 = t->f0; pa.p0 = t->p0; pa.f1 = t->f1; pa.bias = t->stem_b; pa.skip = nullptr; pa.out = t->act[0]; pa.err = t->err;
-        pa.head_w4 = t->n_blocks == 0 ? t->head_w4 : nullptr; pa.head_b4 = t->head_b4; pa.feat = t->feat;
-        int pairs = t->sm_count / 2;
-        if (pairs > pa.n_tiles) pairs = pa.n_tiles;
-        k_conv3x3_pair<<<2 * pairs, TW_THREADS, PR_SMEM_BYTES, S_(stream)>>>(t->pmaps[3], pa);
-        SGO_LAUNCHED(e);
-    } else {
-        k_stem<<<grid, TW_C, 9 * 16 * TW_C * sizeof(float), S_(stream)>>>(boards, d_index, d_sym, n, t->S, t->stem_w, t->stem_b, t->act[0]);
-        SGO_LAUNCHED(e);
+    // stem = im2col from the bitboards + one pair-kernel GEMM (K = 192) with the bias/ReLU epilogue
+    int g2 = n < 8 * t->sm_count ? n : 8 * t->sm_count;
+    k_stem_im2col<<<g2, 256, 0, S_(stream)>>>(boards, d_index, d_sym, n, t->S, t->stem_col);
+    SGO_LAUNCHED(e);
+    {
+        int rc0 = launch_conv(e, t, n, -1, 3, 0, -1, stream, t->n_blocks == 0);
+        if (rc0) return rc0;
     }
     if (prof) cudaEventRecord(pe[1], S_(stream));
     int x = 0;                                     // act[x] holds the block input
@@ -960,33 +564,20 @@ extern "C" int sgo_tower_forward(sgo_engine *e, int32_t slot, int32_t which, con
         int tmp = (x + 1) % 3, y = (x + 2) % 3;
         int rc = launch_conv(e, t, n, 2 * b, x, tmp, -1, stream);           // conv1 + BN + ReLU   (model.py:39-41)
         if (rc) return rc;
-        rc = launch_conv(e, t, n, 2 * b + 1, tmp, y, x, stream, t->use_pair && b == t->n_blocks - 1);   // conv2 + BN + skip + ReLU (model.py:42-45)
+        rc = launch_conv(e, t, n, 2 * b + 1, tmp, y, x, stream, b == t->n_blocks - 1);   // conv2 + BN + skip + ReLU (model.py:42-45)
         if (rc) return rc;
         x = y;
     }
     if (prof) cudaEventRecord(pe[2], S_(stream));
-    HeadArgs h;
-    h.n = n; h.S = t->S; h.W = t->W; h.scatter = scatter; h.index = d_index; h.syms = d_sym; h.act = t->act[x];
-    h.pcw = t->pol_conv_w; h.pcb = t->pol_conv_b; h.pfw = t->pol_fc_w; h.pfb = t->pol_fc_b;
-    h.vcw = t->val_conv_w; h.vcb = t->val_conv_b; h.v1w = t->val_fc1_w; h.v1b = t->val_fc1_b;
-    h.v2w = t->val_fc2_w; h.v2b = t->val_fc2_b; h.policy = d_policy; h.value = d_value;
-    if (t->use_pair) {
-        FcArgs f;
-        f.n = n; f.S = t->S; f.W = t->W; f.scatter = scatter; f.index = d_index; f.syms = d_sym; f.feat = t->feat;
-        f.pfw = t->pol_fc_w; f.pfb = t->pol_fc_b; f.v1w = t->val_fc1_w; f.v1b = t->val_fc1_b; f.v2w = t->val_fc2_w; f.v2b = t->val_fc2_b;
-        f.policy = d_policy; f.value = d_value;
-        int fs = (int)sizeof(float) * (4 * P * FC_PB + FC_PB * e->A + FC_PB * (FC_THREADS / 32));
-        int fgrid = (n + FC_PB - 1) / FC_PB;
-        if (fgrid > 2 * t->sm_count) fgrid = 2 * t->sm_count;
-        k_heads_fc<<<fgrid, FC_THREADS, fs, S_(stream)>>>(f);
-        SGO_LAUNCHED(e);
-    } else {
-        int hs = (HD_P * (4 * P + e->A + 256) + TW_C * 4) * (int)sizeof(float);
-        int hgrid = (n + HD_P - 1) / HD_P;
-        if (hgrid > 4 * t->sm_count) hgrid = 4 * t->sm_count;
-        k_heads<<<hgrid, HD_THREADS, hs, S_(stream)>>>(h);
-        SGO_LAUNCHED(e);
-    }
+    FcArgs f;
+    f.n = n; f.S = t->S; f.W = t->W; f.scatter = scatter; f.index = d_index; f.syms = d_sym; f.feat = t->feat;
+    f.pfw = t->pol_fc_w; f.pfb = t->pol_fc_b; f.v1w = t->val_fc1_w; f.v1b = t->val_fc1_b; f.v2w = t->val_fc2_w; f.v2b = t->val_fc2_b;
+    f.policy = d_policy; f.value = d_value;
+    int fs = (int)sizeof(float) * (4 * P * FC_PB + FC_PB * e->A + FC_PB * (FC_THREADS / 32));
+    int fgrid = (n + FC_PB - 1) / FC_PB;
+    if (fgrid > 2 * t->sm_count) fgrid = 2 * t->sm_count;
+    k_heads_fc<<<fgrid, FC_THREADS, fs, S_(stream)>>>(f);
+    SGO_LAUNCHED(e);
     if (prof) { cudaEventRecord(pe[3], S_(stream)); t->prof_pos[t->prof_n++] = n; }
     return 0;
 }
@@ -1046,13 +637,9 @@ extern "C" int sgo_tower_debug_conv(sgo_engine *e, int32_t slot, int32_t n, int3
 {
     if (slot < 0 || slot > 1 || !e->tower[slot]) return sgo_fail(e, "tower slot has no weights");
     sgo_tower *t = e->tower[slot];
-    if (n < 1 || n > t->max_pos || layer < 0 || layer >= t->n_layers || in < 0 || in > 2 || out < 0 || out > 2 || (skip > 2 && skip < 16))
+    if (n < 1 || n > t->max_pos || layer < 0 || layer >= t->n_layers || in < 0 || in > 2 || out < 0 || out > 2 || skip > 2)
         return sgo_fail(e, "debug_conv arguments out of range");
-    g_conv_variant = skip >= 16 ? (skip >> 4) : 0;      // profiling experiments: variant flags ride in skip's high bits
-    if (skip >= 16) skip = (skip & 15) == 15 ? -1 : (skip & 15);
-    int rc = launch_conv(e, t, n, layer, in, out, skip, stream);
-    g_conv_variant = 0;
-    return rc;
+    return launch_conv(e, t, n, layer, in, out, skip, stream);
 }
 
 // raw activation buffer access (bf16 [n*(W+1)+1][W][C]) for tests
