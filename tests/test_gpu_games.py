@@ -89,3 +89,28 @@ def test_evaluate_runs_two_trees():
     finally:
         conf.clear()
         conf.update(old)
+
+
+def test_selfplay_worker_shim_resume_and_records(tmp_path):
+    """batched NoModelSelfPlayWorker stand-in — dir-skip resume, per-ply samples."""
+    from sejonggo_b200 import selfplay_worker as sw, predicting_queue_worker as pq
+    from sejonggo_b200.conf import conf
+    old = dict(conf)
+    try:
+        conf.update(SIZE=5, ENERGY=4, MCTS_SIMULATIONS=8, KOMI=5.5, SELF_PLAY_DIR=str(tmp_path / "sp"), STOP_EXPLORATION=2,
+                    RESIGNATION_PERCENT=1.0)
+        m = FakeModel("model_9", salt=3, sharp=True)
+        pq.register_models(best=m, latest=m)
+        os.makedirs(tmp_path / "sp" / "model_9" / "game_00001")           # already played elsewhere -> skipped
+        saved = sw.run_selfplay(n_games=4, concurrent=2, size=5, num_moves=6)
+        assert saved == [0, 2, 3]
+        for g in saved:
+            d = tmp_path / "sp" / "model_9" / ("game_%05d" % g)
+            moves = sorted(os.listdir(d))
+            assert moves and moves[0] == "move_000"
+            z = np.load(d / "move_000" / "sample.npz")
+            assert z["board"].shape == (1, 5, 5, 17) and z["policy_target"].shape == (26,)
+            assert float(z["board"][0, 0, 0, 16]) == 1.0 and float(z["board"][..., :16].sum()) == 0.0
+    finally:
+        conf.clear()
+        conf.update(old)
