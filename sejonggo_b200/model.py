@@ -112,13 +112,13 @@ class TowerModel(object):
         self.size = self.params['meta']['size']
         self.max_positions = max_positions
         self._folded = None
-        self._loaded = {}            # id(engine) -> slot
         self._host_engine = None
 
     # ---- engine-side protocol ----------------------------------------------------
     def attach(self, engine, slot=0, max_positions=None):
-        key = (id(engine), slot)
-        if self._loaded.get(key):
+        # which model occupies a weight slot is recorded ON the engine (ids of dead engines get reused)
+        slots = engine.__dict__.setdefault("_tower_slots", {})
+        if slots.get(slot, (None, 0))[0] is self:
             return
         if engine.S != self.size:
             raise EngineError("model is for %dx%d boards, engine is %dx%d" % (self.size, self.size, engine.S, engine.S))
@@ -130,14 +130,14 @@ class TowerModel(object):
             setattr(w, k, v.data_ptr())
         mp = max_positions or self.max_positions
         engine._ck(engine.lib.sgo_tower_load_weights(engine.h, slot, C.byref(w), int(mp), engine._stream()))
-        self._loaded[key] = mp
+        slots[slot] = (self, mp)
         torch.cuda.synchronize(engine.device)
 
     def evaluate(self, engine, which, idx, syms=None, slot=0, out=None):
         """idx int64/int32 device tensor of positions (games / leaf slots); returns compact
         device tensors (policy [k,A] f32, value [k] f32)."""
         self.attach(engine, slot)
-        mp = self._loaded[(id(engine), slot)]
+        mp = engine._tower_slots[slot][1]
         k = int(idx.numel())
         idx32 = idx.to(torch.int32).contiguous()
         sy = None if syms is None else syms.to(torch.int32).contiguous()

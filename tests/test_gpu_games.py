@@ -114,3 +114,60 @@ def test_selfplay_worker_shim_resume_and_records(tmp_path):
     finally:
         conf.clear()
         conf.update(old)
+
+
+def _same_game(got, ref):
+    assert len(got['moves']) == len(ref['moves'])
+    for a, b in zip(got['moves'], ref['moves']):
+        assert a['move'] == b['move'] and a['player'] == b['player'] and a['move_n'] == b['move_n']
+        assert np.array_equal(a['board'], b['board'])
+        assert np.float32(a['value']).view(np.uint32) == np.float32(b['value']).view(np.uint32)
+        assert np.array_equal(np.asarray(a['policy']).view(np.uint64), np.asarray(b['policy']).view(np.uint64))
+    assert got['result'] == ref['result'] and got['winner'] == ref['winner'] and got['winner_model'] == ref['winner_model']
+    assert got['modelB_name'] == ref['modelB_name'] and got['modelW_name'] == ref['modelW_name']
+
+
+def test_match_play_with_random_symmetries_vs_oracle():
+    """BASELINE config 4 semantics (evaluator.py:23-36): two models, two trees, stop_exploration=0, one of the
+    7 symmetries drawn per predict batch (incl. the Q8 rot90/270 quirk) — engine vs oracle, 6 concurrent games."""
+    from sejonggo_b200 import self_play as sp
+    from sejonggo_b200.conf import conf
+    S, batch, sims, G = 9, 8, 24, 6
+    old = dict(conf)
+    try:
+        conf.update(SIZE=S, MCTS_BATCH_SIZE=batch, KOMI=5.5)
+        best, tested = FakeModel("best", salt=11, sharp=True), FakeModel("tested", salt=12, sharp=True)
+        games = sp.play_games(best, tested, G, sims, 0, self_play=False, num_moves=9,
+                              rngs=[gl.SeededRng(70 + g) for g in range(G)], use_symmetry=True)
+    finally:
+        conf.clear()
+        conf.update(old)
+    for g in range(G):
+        b, t = FakeModel("best", salt=11, sharp=True), FakeModel("tested", salt=12, sharp=True)
+        ref = gl.play_game(b, t, sims, 0, self_play=False, num_moves=9, size=S, mcts_batch_size=batch, rng=gl.SeededRng(70 + g))
+        _same_game(games[g], ref)
+
+
+def test_mode_b_selfplay_with_symmetries_vs_oracle():
+    """main_selfplay.py's path: play_game_async("BEST_SYM","BEST_SYM") — every request (root and leaves) draws a
+    symmetry; engine (exact RNG order) vs oracle, 4 concurrent games on 7x7."""
+    from sejonggo_b200 import nomodel_self_play as nsp, predicting_queue_worker as pq
+    from sejonggo_b200.conf import conf
+    from oracle.fake_eval import evaluate
+    S, energy, sims, G = 7, 8, 24, 4
+    old = dict(conf)
+    try:
+        conf.update(SIZE=S, ENERGY=energy, MCTS_SIMULATIONS=sims, KOMI=5.5)
+        m = FakeModel("model_1", salt=21, sharp=True)
+        pq.register_models(best=m, latest=m)
+        games = nsp.play_games_async("BEST_SYM", "BEST_SYM", G, energy, 3, self_play=True, num_moves=8,
+                                     rngs=[gl.SeededRng(90 + g) for g in range(G)])
+    finally:
+        conf.clear()
+        conf.update(old)
+    for g in range(G):
+        mm = FakeModel("model_1", salt=21, sharp=True)
+        ref = gl.play_game_async("BEST_SYM", "BEST_SYM", energy, 3, 0, self_play=True, num_moves=8, size=S, conf_sims=sims,
+                                 conf_energy=energy, rng=gl.SeededRng(90 + g), names={"BEST_SYM": "model_1"},
+                                 predict=lambda tag, b, sym: (lambda p, v: (p[0], v[0]))(*gl.sym_predict(mm, b, sym)))
+        _same_game(games[g], ref)
