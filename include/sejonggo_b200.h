@@ -151,6 +151,8 @@ int sgo_tower_free(sgo_engine *e, int32_t slot);
  * compact (i) or scattered to d_index[i] when scatter != 0 */
 int sgo_tower_forward(sgo_engine *e, int32_t slot, int32_t which, const int32_t *d_index, int32_t n,
                       const int32_t *d_sym, int32_t scatter, float *d_policy, float *d_value, void *stream);
+/* positions one forward of this slot can take (0 = no weights loaded) */
+int sgo_tower_max_positions(sgo_engine *e, int32_t slot);
 /* sticky tower error flags (16 = an mbarrier wait timed out); synchronises */
 int sgo_tower_check_sync(sgo_engine *e, int32_t slot, int32_t *h_flags, void *stream);
 /* live CUDA-event timing of the tower kernels on the launching stream (bench.py roofline):
@@ -161,6 +163,24 @@ int sgo_tower_profile_read_sync(sgo_engine *e, int32_t slot, double *h_out);
  * bf16 [n*(S-1)+1][S-2][C] (row 0 and every (S-1)-th row are zero padding) */
 int sgo_tower_debug_conv(sgo_engine *e, int32_t slot, int32_t n, int32_t layer, int32_t in, int32_t out, int32_t skip, void *stream);
 int sgo_tower_act_copy(sgo_engine *e, int32_t slot, int32_t buf, int32_t n, void *d_data, int32_t to_tower, void *stream);
+
+/* ---- the per-step driver: one MCTS search step of EVERY game in one call ------------------
+ * mode 0 = self_play.simulate (self_play.py:28-120): select top-`leaves` + greedy descents,
+ *          one evaluation of all leaves, expand + backup in rank order;
+ * mode 1 = one nomodel_self_play.async_simulate2 wave (nomodel_self_play.py:59-82): `leaves`
+ *          (= ENERGY) busy-flag selections, evaluation, expand, resumed while any game reports
+ *          "No best leaf", then the FIFO back-propagation of `total_energy` results.
+ * Leaves are evaluated by the network slot d_model_of_game[g] (NULL = slot 0 for every game)
+ * with symmetry ids d_sym_game[g] (symmetry.random_symmetry_predict, one draw per game per
+ * batch; NULL = identity).  *h_leaves_done = simulations performed (synchronises). */
+int sgo_selfplay_step(sgo_engine *e, int32_t mode, const int32_t *d_tree_sel, const int32_t *d_model_of_game,
+                      int32_t leaves, int32_t total_energy, const int32_t *d_sym_game, int32_t *h_leaves_done, void *stream);
+/* self_play.py:203-214 move_data for every game, packed: uint32 [G][sgo_record_words()] =
+ * board (16 x ceil(S*S/32) plane words + to_move), move index, value (f32 bits), tree-valid
+ * flag, policy_target = root priors as f32 [S*S+1] (Q14).  d_moves / d_values may be NULL. */
+int sgo_record_words(sgo_engine *e);
+int sgo_records_pack(sgo_engine *e, const int32_t *d_tree_sel, const int32_t *d_moves, const float *d_values,
+                     uint32_t *d_out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -77,7 +77,7 @@ class BatchedGames(object):
     def __init__(self, models, n_games, size=19, mode='a', mcts_batch_size=100, energy=8, mcts_simulations=1600,
                  stop_exploration=30, self_play=False, num_moves=None, resign=(None, None), komi=5.5,
                  dirichlet_eps=0.25, use_symmetry=True, root_symmetry=None, rng=None, rngs=None, arena_blocks=None,
-                 device=0, record_boards='full', engine=None):
+                 device=0, record_boards='full', engine=None, native_step=True):
         """models: (model1, model2); pass the same object twice for self-play.
         resign: (resign_model1, resign_model2), each None, a float, or an array[G].
         rngs: optional list of per-game rng objects (parity runs); else one shared `rng`."""
@@ -111,6 +111,8 @@ class BatchedGames(object):
         self.resign = [self._per_game(resign[0]), self._per_game(resign[1])]
         # device fast path: every evaluator is a GPU tower and draws are not injected per game
         self.fast = all(hasattr(ev, "is_sgo_evaluator") for ev in self.ev) and rngs is None
+        # with GPU towers the whole search step runs inside the library (sgo_selfplay_step)
+        self.native_step = native_step and self.fast and all(hasattr(ev, "attach") for ev in self.ev)
         self.sim_count = 0            # leaves expanded + backed up (the north-star "simulations")
         self.eval_count = 0
         self.plies_done = 0
@@ -252,6 +254,17 @@ class BatchedGames(object):
         g = torch.Generator(device=self.eng.device).manual_seed(seed)
         return torch.randint(0, 7, (self.G,), generator=g, device=self.eng.device, dtype=torch.int32)
 
+    def _search_native(self, tree_sel_dev, cur_model_dev):
+        """The search of one ply through sgo_selfplay_step: the host only loops over steps/waves."""
+        e = self.eng
+        for mi in ((0,) if self.same_model else (0, 1)):
+            self.ev[mi].attach(e, mi)
+        mg = None if self.same_model else cur_model_dev.to(torch.int32)
+        for _ in range(int(self.sims / self.batch)):
+            n = e.selfplay_step(self.mode, self.batch, self.energy, tree_sel_dev, mg, self._draw_syms_device())
+            self.sim_count += n
+            self.eval_count += n
+
     def _search_a_device(self, tree_sel_dev, cur_model_dev):
         e = self.eng
         for _ in range(int(self.sims / self.batch)):
@@ -349,7 +362,9 @@ class BatchedGames(object):
             ts_dev = e.dev(tree_sel, torch.int32)
             cm_dev = e.dev(cur_model, torch.int64)
             self.h2d_bytes += tree_sel.nbytes + cur_model.nbytes
-            if self.mode == 'a':
+            if self.native_step:
+                self._search_native(ts_dev, cm_dev)
+            elif self.mode == 'a':
                 self._search_a_device(ts_dev, cm_dev)
             else:
                 self._search_b_device(ts_dev, cm_dev)
@@ -363,7 +378,8 @@ class BatchedGames(object):
         forced = None
         u01 = None
         prior_h = None
-        if record:
+        packed_rec = record and self.record_boards == 'packed'
+        if record and not packed_rec:
             prior, count, _ = e.child_stats(tree_sel, want=("prior", "count"))
             prior_h = prior.cpu().numpy()                       # policy_target = root priors (Q14)
             self.d2h_bytes += prior_h.nbytes
@@ -371,7 +387,7 @@ class BatchedGames(object):
             u01 = np.array([self.rngs[0].uniform() for _ in range(G)], np.float64)    # device-side sampling
             self.h2d_bytes += u01.nbytes
         elif temperature == 1:
-            if not record:
+            if not record or packed_rec:
                 _, count, _ = e.child_stats(tree_sel, want=("count",))
             count_h = count.cpu().numpy()
             forced = np.full(G, -1, np.int32)
@@ -386,8 +402,13 @@ class BatchedGames(object):
         boards_h = None
         if record and self.record_boards == 'full':
             boards_h = e.export_boards().cpu().numpy()
-        elif record and self.record_boards == 'packed':
-            boards_h = e.export_packed(0).cpu().numpy().view(np.uint32)
+        elif packed_rec:
+            # one packed row per game: board words, move, value, policy_target (sgo_records_pack)
+            rec_h = e.records_pack(tree_sel, index_dev, value).cpu().numpy().view(np.uint32)
+            PW = e.packed_words
+            boards_h = rec_h[:, :PW]
+            prior_h = rec_h[:, PW + 3:PW + 3 + A].view(np.float32)
+            self.d2h_bytes += rec_h.nbytes - boards_h.nbytes
         if boards_h is not None:
             self.d2h_bytes += boards_h.nbytes
         apply = np.full(G, -1, np.int32)

@@ -21,6 +21,8 @@ struct sgo_engine {
     int32_t *err_flags;           // [1] sticky device error bits
     int32_t *counters;            // [4] device scratch counters
     int32_t *h_pinned;            // [8] pinned host mirror
+    float *step_policy, *step_value;   // [G*L][A], [G*L] evaluator outputs of the current step (driver.cu, lazily allocated)
+    int32_t *step_index, *step_sym;    // [G*L] compacted leaf slots awaiting evaluation and their symmetry ids
     struct sgo_tower *tower[2];   // network weight slots (tower.cu): 0 = model1/best, 1 = model2/tested
     unsigned long long launches;  // kernels launched through the ABI (bench.py gpu_launches)
     std::string last_error;

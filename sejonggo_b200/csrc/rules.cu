@@ -278,6 +278,7 @@ extern "C" int sgo_create(const sgo_config *cfg, sgo_engine **out)
     e->S = cfg->size; e->A = cfg->size * cfg->size + 1; e->G = cfg->n_games; e->T = cfg->trees_per_game;
     e->L = cfg->max_leaves; e->NB = cfg->arena_blocks;
     e->tower[0] = e->tower[1] = nullptr;
+    e->step_policy = e->step_value = nullptr; e->step_index = e->step_sym = nullptr;
     e->launches = 0;
     *out = e;
     SGO_CUDA_OK(e, cudaSetDevice(cfg->device));
@@ -317,6 +318,7 @@ extern "C" int sgo_destroy(sgo_engine *e)
     sgo_tower_free(e, 1);
     cudaFree(e->boards); cudaFree(e->leaf_boards); cudaFree(e->leaf_refs); cudaFree(e->leaf_count);
     cudaFree(e->leaf_masks); cudaFree(e->arena); cudaFree(e->meta); cudaFree(e->root_p64);
+    cudaFree(e->step_policy); cudaFree(e->step_value); cudaFree(e->step_index); cudaFree(e->step_sym);
     cudaFree(e->wave); cudaFree(e->err_flags); cudaFree(e->counters); cudaFreeHost(e->h_pinned);
     delete e;
     return 0;

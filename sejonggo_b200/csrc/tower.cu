@@ -510,6 +510,12 @@ extern "C" int sgo_tower_load_weights(sgo_engine *e, int32_t slot, const sgo_tow
     return 0;
 }
 
+extern "C" int sgo_tower_max_positions(sgo_engine *e, int32_t slot)
+{
+    if (slot < 0 || slot > 1 || !e->tower[slot]) return 0;
+    return e->tower[slot]->max_pos;
+}
+
 // one launch of the pair kernel: a tower conv layer (layer >= 0) or the stem GEMM (layer < 0)
 static int launch_conv(sgo_engine *e, sgo_tower *t, int n, int layer, int in, int out, int skip, void *stream, bool heads = false)
 {

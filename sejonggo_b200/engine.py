@@ -216,6 +216,30 @@ class Engine(object):
         self._ck(self.lib.sgo_leaf_compact_sync(self.h, self._p(self._compact_buf), C.byref(n), self._stream()))
         return self._compact_buf[:n.value], n.value
 
+    def selfplay_step(self, mode, leaves, total_energy=0, tree_sel=None, model_of_game=None, sym_game=None):
+        """One search step of every game inside the library (select -> evaluate on the loaded
+        network slot(s) -> expand -> backup).  mode 'a' = self_play.simulate, 'b' = one
+        async_simulate2 wave.  Returns the number of simulations performed."""
+        ts = self.dev(tree_sel, torch.int32)
+        mg = self.dev(model_of_game, torch.int32)
+        sg = self.dev(sym_game, torch.int32)
+        n = C.c_int32(0)
+        self._ck(self.lib.sgo_selfplay_step(self.h, 0 if mode in (0, 'a') else 1, self._p(ts), self._p(mg), int(leaves),
+                                            int(total_energy), self._p(sg), C.byref(n), self._stream()))
+        return n.value
+
+    def record_words(self):
+        return int(self.lib.sgo_record_words(self.h))
+
+    def records_pack(self, tree_sel=None, moves=None, values=None):
+        """uint32 [G][record_words()] packed move_data rows (board, move, value, valid, policy_target)."""
+        ts = self.dev(tree_sel, torch.int32)
+        mv = self.dev(moves, torch.int32)
+        vl = self.dev(values, torch.float32)
+        out = torch.empty((self.G, self.record_words()), dtype=torch.int32, device=self.device)
+        self._ck(self.lib.sgo_records_pack(self.h, self._p(ts), self._p(mv), self._p(vl), self._p(out), self._stream()))
+        return out
+
     def tree_valid(self, tree_sel=None):
         ts = self.dev(tree_sel, torch.int32)
         out = torch.empty((self.G,), dtype=torch.int32, device=self.device)
