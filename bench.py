@@ -217,12 +217,25 @@ def run_ours(a):
     if world > 1:
         sd.broadcast_params(params, src=0, device=dev)           # NCCL weight broadcast
     m = model.TowerModel("model_1", params=params, max_positions=a.max_positions)
-    arena = a.arena or 4 * (SIMS + batch)
-    bg = BatchedGames((m, m), G, size=SIZE, mode=a.mode, mcts_batch_size=BATCH_A, energy=ENERGY_B, mcts_simulations=a.sims,
-                      stop_exploration=30, self_play=True, rng=HostRng(1234 + rank), arena_blocks=arena, device=local,
-                      record_boards='packed')
+    if a.match:
+        # BASELINE.json configs[3] / SURVEY §8d config 4: evaluator.evaluate semantics — two weight sets, two trees
+        # per game, no noise, temperature 0 from ply 0, 1600 sims/ply, one random symmetry per predict batch
+        params2 = model.init_params(SIZE, a.blocks, seed=1)
+        m2 = model.TowerModel("model_2", params=params2, max_positions=a.max_positions)
+        arena = a.arena or 2 * (a.sims + batch)
+        bg = BatchedGames((m, m2), G, size=SIZE, mode=a.mode, mcts_batch_size=BATCH_A, energy=ENERGY_B, mcts_simulations=a.sims,
+                          stop_exploration=0, self_play=False, rng=HostRng(1234 + rank), arena_blocks=arena, device=local,
+                          record_boards='packed')
+    else:
+        m2 = m
+        arena = a.arena or 4 * (SIMS + batch)
+        bg = BatchedGames((m, m), G, size=SIZE, mode=a.mode, mcts_batch_size=BATCH_A, energy=ENERGY_B, mcts_simulations=a.sims,
+                          stop_exploration=30, self_play=True, rng=HostRng(1234 + rank), arena_blocks=arena, device=local,
+                          record_boards='packed')
     e = bg.eng
     m.attach(e, 0)
+    if a.match:
+        m2.attach(e, 1)
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -255,9 +268,15 @@ def run_ours(a):
     if rank == 0:
         sampler.start()
     m.profile(e, 0, True)
+    if a.match:
+        m2.profile(e, 1, True)
     r = timed(a.steps, record=False)
     prof = m.profile_read(e, 0)
     m.profile(e, 0, False)
+    if a.match:
+        p2 = m2.profile_read(e, 1)
+        m2.profile(e, 1, False)
+        prof = {k: prof[k] + p2[k] for k in prof}
     clocks = sampler.stop() if rank == 0 else None
     r2 = timed(a.steps, record=True)                               # end-to-end through the public batched API
     e.check_errors()
@@ -281,11 +300,13 @@ def run_ours(a):
         metric="selfplay_mcts_simulations_per_sec", value=r['sims'] / (r['ms'] * 1e-3), unit="simulations/s", n_gpus=world,
         steps=a.steps, warmup=a.warmup, ms_per_step=r['ms'] / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
         dtype="bf16", data="synthetic",
-        config=dict(workload="19x19 self-play, conf.py default tower (%d blocks x 256 ch, random init), %d sims/ply, %d concurrent "
-                             "games per GPU, mode %s" % (a.blocks, a.sims, G, a.mode.upper()),
+        config=dict(workload=("19x19 %s, conf.py default tower (%d blocks x 256 ch, random init), %d sims/ply, %d concurrent "
+                              "games per GPU, mode %s") % ("match play (evaluator.evaluate: two weight sets, two trees per game, "
+                                                           "temperature 0, random symmetry per batch)" if a.match else "self-play",
+                                                           a.blocks, a.sims, G, a.mode.upper()),
                     games_per_gpu=G, mode=a.mode, sims_per_ply=a.sims, moves_per_sec=r['plies'] / (r['ms'] * 1e-3),
                     l2="working set (trees %.1f GB, activations %.1f GB) >> 126 MB L2; no flush needed" %
-                       (G * 2 * arena * 6272 / 1e9, 3 * (a.max_positions * 18 + 1) * 17 * 512 / 1e9),
+                       (G * bg.eng.T * 2 * arena * 6272 / 1e9, 3 * (a.max_positions * 18 + 1) * 17 * 512 / 1e9),
                     step="one ply of every game", parallelism="games sharded, %d rank(s)" % world,
                     records_gathered=None if gathered is None else [int(g.numel()) for g in gathered]),
         e2e=dict(value=r2['sims'] / (r2['ms'] * 1e-3), unit="simulations/s", h2d_bytes_per_step=r2['h2d'] / a.steps,
@@ -312,12 +333,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="a", choices=["a", "b"])
     ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
-    ap.add_argument("--sims", type=int, default=SIMS)
+    ap.add_argument("--sims", type=int, default=None)
+    ap.add_argument("--match", action="store_true", help="SURVEY §8d config 4: match play, two models, 1600 sims/ply")
     ap.add_argument("--blocks", type=int, default=BLOCKS)
     ap.add_argument("--max-positions", type=int, default=16384)
     ap.add_argument("--arena", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
+    if a.sims is None:
+        a.sims = 1600 if a.match else SIMS
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -77,11 +77,13 @@ class BatchedGames(object):
     def __init__(self, models, n_games, size=19, mode='a', mcts_batch_size=100, energy=8, mcts_simulations=1600,
                  stop_exploration=30, self_play=False, num_moves=None, resign=(None, None), komi=5.5,
                  dirichlet_eps=0.25, use_symmetry=True, root_symmetry=None, rng=None, rngs=None, arena_blocks=None,
-                 device=0, record_boards='full', engine=None, native_step=True):
+                 device=0, record_boards='full', engine=None, native_step=True, names=None):
         """models: (model1, model2); pass the same object twice for self-play.
         resign: (resign_model1, resign_model2), each None, a float, or an array[G].
         rngs: optional list of per-game rng objects (parity runs); else one shared `rng`."""
         self.m1, self.m2 = models
+        # names reported in game_data; given explicitly when a tag resolves to another model's network (Q21)
+        self.names = names or (getattr(self.m1, "name", "model1"), getattr(self.m2, "name", "model2"))
         self.same_model = self.m1 is self.m2
         self.ev = [as_evaluator(self.m1), as_evaluator(self.m1) if self.same_model else as_evaluator(self.m2)]
         if self.same_model:
@@ -451,7 +453,7 @@ class BatchedGames(object):
         sc = e.score().cpu().numpy()
         ps = {1: "B", 0: "D", -1: "W"}
         out = []
-        n1, n2 = getattr(self.m1, "name", "model1"), getattr(self.m2, "name", "model2")
+        n1, n2 = self.names
         for g in range(self.G):
             black, white = float(sc[g, 1]), float(sc[g, 2]) + self.komi
             winner = 1 if black > white else (0 if black == white else -1)

@@ -22,6 +22,10 @@ conf = {
     'EVALUATE_MARGIN': .55,
     'PREDICTING_BATCH_SIZE': 32,
     'SELF_PLAY_DIR': 'sp_self_play_data',
+    'MODEL_DIR': 'sp_models',
+    'EVAL_DIR': 'sp_eval_games',
+    'GAMES_DIR': 'sp_eval_games',
+    'BEST_MODEL': 'best_model.npz',      # the reference's best_model.h5 (Keras .h5 I/O is out of scope)
     # engine-only knobs
     'CONCURRENT_GAMES': 1024,
     'ARENA_BLOCKS': None,

@@ -11,6 +11,7 @@ or from a dict in the same layout.
 """
 import ctypes as C
 import math
+import os
 import numpy as np
 import torch
 
@@ -166,6 +167,10 @@ class TowerModel(object):
         return dict(stem_ms=out[0], conv_ms=out[1], heads_ms=out[2], conv_launches=int(out[3]), positions=int(out[4]),
                     forwards=int(out[5]))
 
+    def save(self, path):
+        """Keras model.save (evaluator.py:20, model.py:117-119) for the .npz weight files."""
+        save_params(path, self.params, self.name)
+
     # ---- reference protocol (self_play.py:70,187) ----------------------------------
     def predict_on_batch(self, X):
         X = np.asarray(X)
@@ -177,6 +182,72 @@ class TowerModel(object):
         idx = torch.arange(n, dtype=torch.int32, device=e.device)
         p, v = self.evaluate(e, 0, idx, None, slot=0)
         return p.cpu().numpy(), v.cpu().numpy().reshape(n, 1)
+
+
+# ---- weight files: the reference keeps Keras .h5 files in MODEL_DIR (model.py:96-160); here the same
+# directory protocol with .npz files of the params dict ("model_<n>.npz", BEST_MODEL) -----------------
+def save_params(path, params, name):
+    flat = {'__name__': np.array(name), '__meta__': np.array([params['meta']['size'], params['meta']['n_blocks'],
+                                                              params['meta'].get('seed', 0)], np.int64)}
+    for k, v in params.items():
+        if k == 'meta':
+            continue
+        if isinstance(v, dict):
+            for kk, vv in v.items():
+                flat["%s/%s" % (k, kk)] = vv.numpy()
+        else:
+            flat[k] = v.numpy()
+    with open(path, 'wb') as f:                  # a file object: numpy must not append ".npz" to BEST_MODEL-style names
+        np.savez(f, **flat)
+
+
+def load_params(path):
+    z = np.load(path)
+    size, n_blocks, seed = (int(x) for x in z['__meta__'])
+    p = {'meta': dict(size=size, n_blocks=n_blocks, seed=seed)}
+    for k in z.files:
+        if k.startswith('__'):
+            continue
+        t = torch.from_numpy(np.array(z[k]))
+        if '/' in k:
+            a, b = k.split('/')
+            p.setdefault(a, {})[b] = t
+        else:
+            p[k] = t
+    return str(z['__name__']), p
+
+
+def load_model_by_name(filename, **kw):
+    """model.py:157: a TowerModel from MODEL_DIR/<filename>."""
+    name, params = load_params(os.path.join(conf['MODEL_DIR'], filename))
+    return TowerModel(name, params=params, **kw)
+
+
+def load_latest_model(**kw):
+    """model.py:122-141: the highest-numbered model_<n> file in MODEL_DIR."""
+    index, best = -1, None
+    for filename in os.listdir(conf['MODEL_DIR']):
+        try:
+            i = int(filename.split('.')[0].split('_')[-1])
+        except ValueError:
+            continue
+        if i > index:
+            index, best = i, filename
+    if best is None:
+        raise FileNotFoundError("no model_<n> file in %s" % conf['MODEL_DIR'])
+    return load_model_by_name(best, **kw)
+
+
+def load_best_model(**kw):
+    """model.py:144-155: BEST_MODEL, or a fresh model_1 when there is none yet."""
+    path = os.path.join(conf['MODEL_DIR'], conf['BEST_MODEL'])
+    if os.path.isfile(path):
+        return load_model_by_name(conf['BEST_MODEL'], **kw)
+    os.makedirs(conf['MODEL_DIR'], exist_ok=True)
+    m = build_model("model_1")
+    m.save(os.path.join(conf['MODEL_DIR'], "model_1.npz"))
+    m.save(path)
+    return m
 
 
 def build_model(name, size=None, n_blocks=None, seed=0):

@@ -23,6 +23,7 @@ def play_games_async(model1_indicator, model2_indicator, n_games, energy, stop_e
                      record_boards='full', arena_blocks=None, device=0, exact_rng_order=True):
     m1 = _Tagged(model1_indicator)
     m2 = m1 if model2_indicator == model1_indicator else _Tagged(model2_indicator)
+    names = (m1.name, m2.name)            # put_name_request: LATEST_SYM reports the latest model's name (:110-113)
     # an evaluator object can be shared when both tags resolve to one network
     if hasattr(m1.model, "is_sgo_evaluator"):
         m1 = m1.model
@@ -33,7 +34,7 @@ def play_games_async(model1_indicator, model2_indicator, n_games, energy, stop_e
                       stop_exploration=stop_exploration, self_play=self_play, num_moves=num_moves,
                       resign=(resign_model1, resign_model2), komi=conf['KOMI'], dirichlet_eps=conf['DIRICHLET_EPSILON'],
                       use_symmetry=sym, rng=rng, rngs=rngs, arena_blocks=arena_blocks or conf['ARENA_BLOCKS'],
-                      device=device, record_boards=record_boards)
+                      device=device, record_boards=record_boards, names=names)
     bg.energy = conf['ENERGY']          # wave count and final back-props read conf (:116, :80)
     return bg.run(exact_rng_order=exact_rng_order)
 

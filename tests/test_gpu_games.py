@@ -171,3 +171,88 @@ def test_mode_b_selfplay_with_symmetries_vs_oracle():
                                  conf_energy=energy, rng=gl.SeededRng(90 + g), names={"BEST_SYM": "model_1"},
                                  predict=lambda tag, b, sym: (lambda p, v: (p[0], v[0]))(*gl.sym_predict(mm, b, sym)))
         _same_game(games[g], ref)
+
+
+def test_run_evaluation_bookkeeping(tmp_path):
+    """evaluate_worker.run_evaluation: claims EVAL_DIR/<latest>/game_%03d, plays the claimed games concurrently,
+    touches the winner file; eval_statistic reads it back; a second worker finds nothing left (modes A and B)."""
+    from sejonggo_b200 import evaluate_worker as ew, evaluator
+    from sejonggo_b200.conf import conf
+    old = dict(conf)
+    try:
+        for mode, latest_name in (('a', "model_2"), ('b', "model_3")):
+            conf.update(SIZE=9, MCTS_BATCH_SIZE=8, ENERGY=8, MCTS_SIMULATIONS=16, KOMI=5.5, EVALUATE_N_GAMES=6,
+                        EVAL_DIR=str(tmp_path / "eval"), GAMES_DIR=str(tmp_path / "games"), MODEL_DIR=str(tmp_path / "models"))
+            best, latest = FakeModel("model_1", salt=1, sharp=True), FakeModel(latest_name, salt=2, sharp=True)
+            os.makedirs(os.path.join(conf['EVAL_DIR'], latest_name, "game_004"))          # taken by another worker
+            wins, total = ew.run_evaluation(best, latest, concurrent=4, mode=mode, num_moves=12)
+            assert total == 5 and 0 <= wins <= 5
+            stat = evaluator.eval_statistic()
+            assert abs(stat[latest_name] - wins / 6.0) < 1e-12                             # game_004 counts as played, not won
+            for g in (0, 1, 2, 3, 5):
+                files = os.listdir(os.path.join(conf['EVAL_DIR'], latest_name, "game_%03d" % g))
+                assert len(files) == 1 and files[0] in ("model_1", latest_name, "None")
+            assert ew.run_evaluation(best, latest, concurrent=4, mode=mode, num_moves=12) == (0, 0)
+            if mode == 'b':                                                                # eval games double as training data
+                assert os.path.isdir(os.path.join(conf['GAMES_DIR'], latest_name, "eval_game_000", "move_000"))
+        assert ew.run_evaluation(best, best, mode='a') == (0, 0)                           # "No new trained model"
+    finally:
+        conf.clear()
+        conf.update(old)
+
+
+def test_gtp_engine_matches_oracle_search():
+    """sejonggo.GTPEngine (batch of one): genmove = root eval + new tree + sims/B simulate steps + T=0 pick, with the
+    tree re-rooted by play/genmove — every generated move equals the oracle's mode-A search on the same position."""
+    from sejonggo_b200 import sejonggo as gtp
+    from sejonggo_b200.conf import conf
+    from oracle import oracle as o
+    S, B, SIMS = 9, 8, 32
+    old = dict(conf)
+    try:
+        conf.update(SIZE=S, MCTS_BATCH_SIZE=B, MCTS_SIMULATIONS=SIMS, KOMI=5.5)
+        model = FakeModel("model_7", salt=11, sharp=True)
+        g = gtp.GTPEngine(model=model, mcts_simulations=SIMS, size=S, mcts_batch_size=B, use_symmetry=False)
+        assert g.parse_command("protocol_version") == "= 2\n\n"
+        assert g.parse_command("name") == "= SejongGo - model_7 - 32 simulations\n\n"
+        assert g.parse_command("boardsize 9") == "=\n\n"
+        with pytest.raises(Exception):
+            g.parse_command("boardsize 19")
+        assert g.parse_move("A9") == (0, 0) and g.parse_move("J1") == (8, 8) and g.parse_move("pass") == (0, S)
+        assert g.print_move(0, 0) == "A9" and g.print_move(8, 8) == "J1"
+        # oracle side: the same game, searching each genmove from scratch or from the kept subtree
+        om = FakeModel("model_7", salt=11, sharp=True)
+        board, _ = o.game_init(S)
+        tree = None
+
+        def reroot(t, index):                      # sejonggo.py:38-43
+            c = t.child(index) if t is not None else None
+            return c.detach() if c is not None else None
+
+        script = [("play", "B", "E5"), ("genmove", "W"), ("play", "B", "C3"), ("genmove", "W"), ("genmove", "B"), ("play", "W", "pass"),
+                  ("genmove", "B")]
+        for cmd in script:
+            if cmd[0] == "play":
+                x, y = g.parse_move(cmd[2])
+                index = S * S if y == S else y * S + x
+                assert g.parse_command("play %s %s" % (cmd[1], cmd[2])) == "=\n\n"
+                tree = reroot(tree, index)
+                o.make_play(x, y, board, gtp.COLOR_TO_PLAYER[cmd[1]])
+            else:
+                p, v = om.predict_on_batch(board)
+                if tree is None or tree.nchild == 0:
+                    tree = o.new_tree(p[0], board)
+                for _ in range(SIMS // B):
+                    o.simulate(tree, np.copy(board), lambda b: om.predict_on_batch(b), B, int(board[0, 0, 0, 16]))
+                index = o.pick_t0(tree)
+                x, y = index % S, index // S
+                out = g.parse_command("genmove %s" % cmd[1])
+                assert out == "= %s\n\n" % g.print_move(x, y), (cmd, out)
+                tree = reroot(tree, index)
+                o.make_play(x, y, board, gtp.COLOR_TO_PLAYER[cmd[1]])
+            assert np.array_equal(g.board, board), cmd
+        assert g.parse_command("clear_board") == "=\n\n"
+        assert np.array_equal(g.board, o.game_init(S)[0])
+    finally:
+        conf.clear()
+        conf.update(old)
