@@ -22,13 +22,19 @@
 #define PR_B_BYTES (128 * 128)
 #define PR_STAGE_BYTES (PR_A_BYTES + PR_B_BYTES)
 
+#define PR_MAXH 8
 struct PairMaps {
     CUtensorMap full0, part0, part1, full1;   // activation boxes: (64, W, f0), (64, p0, 1), (64, W-p0, 1), (64, W, f1)
     CUtensorMap w;                            // weights box (64 ci, 128 co)
+    CUtensorMap fullh[PR_MAXH];               // real-row tiling: (64, W, h) for h = 1..PR_MAXH (a run of rows inside ONE position)
 };
 
 struct PairArgs {
     int W, RT, rows_per_pos, YB, n_tiles, w_row0, relu;
+    // rr != 0: a tile is RT consecutive REAL pixel rows (pad rows are skipped, no MAC is spent on them): tile row i of tile t
+    // is real row R = t*RT + i = (pos, y) at padded row pos*rows_per_pos + 1 + y; a tile crosses at most one position
+    // boundary (needs RT <= W), so each CTA's full rows are one or two row runs.  n_real = positions * W.
+    int rr, n_real;
     int n_taps, kchunks;      // 9 x 4 for the tower convs; 1 x 3 for the stem GEMM over the im2col tensor
     int f0, p0, f1;           // rank 0: f0 full rows + p0 pixels of row f0; rank 1: (W-p0) pixels of row f0 (if p0) + f1 full rows
     const float *bias;
@@ -113,6 +119,8 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&maps.full0) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&maps.full1) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&maps.w) : "memory");
+        if (a.rr)
+            for (int h = 0; h < PR_MAXH; h++) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&maps.fullh[h]) : "memory");
         for (int s = 0; s < PR_STAGES; s++) { mbar_init(&tail->full[s], 1); mbar_init(&tail->empty[s], 1); }
         for (int s = 0; s < 2; s++) { mbar_init(&tail->tmem_full[s], 1); mbar_init(&tail->tmem_empty[s], 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -139,6 +147,13 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
             bool ok = true;
             for (int tile = pair; tile < a.n_tiles && ok; tile += n_pairs) {
                 int yb0 = tile * a.RT;
+                int h1 = a.RT;                                    // tile rows inside the first position
+                if (a.rr) {
+                    int pos0 = yb0 / a.W, y0 = yb0 - pos0 * a.W;
+                    h1 = a.W - y0 < a.RT ? a.W - y0 : a.RT;
+                    yb0 = pos0 * a.rows_per_pos + 1 + y0;         // padded row of tile row 0; tile row i -> yb0 + i + (i >= h1)
+                }
+                const int r1s = a.f0 + (a.p0 ? 1 : 0);            // first full tile row of rank 1
                 for (int tap = 0; tap < a.n_taps && ok; tap++) {
                     int dy = a.n_taps == 1 ? 0 : tap / 3 - 1, dx = a.n_taps == 1 ? 0 : tap % 3 - 1;
                     for (int kc = 0; kc < a.kchunks; kc++) {
@@ -148,12 +163,26 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
                         uint64_t *fb = &tail->full[stage];
                         if (rank == 0) {
                             mbar_expect_tx(fb, a_bytes0 + a_bytes1 + 2 * PR_B_BYTES);     // bytes of BOTH CTAs
-                            tma2_load_3d(sa, &maps.full0, kc * TW_KCH, dx, yb0 + dy, fb);
-                            if (a.p0) tma2_load_3d(sa + (size_t)a.f0 * a.W * 128, &maps.part0, kc * TW_KCH, dx, yb0 + a.f0 + dy, fb);
+                            if (h1 >= a.f0) {
+                                tma2_load_3d(sa, &maps.full0, kc * TW_KCH, dx, yb0 + dy, fb);
+                            } else {                                                      // the position boundary cuts this rank's rows
+                                tma2_load_3d(sa, &maps.fullh[h1 - 1], kc * TW_KCH, dx, yb0 + dy, fb);
+                                tma2_load_3d(sa + (size_t)h1 * a.W * 128, &maps.fullh[a.f0 - h1 - 1], kc * TW_KCH, dx, yb0 + h1 + 1 + dy, fb);
+                            }
+                            if (a.p0) tma2_load_3d(sa + (size_t)a.f0 * a.W * 128, &maps.part0, kc * TW_KCH, dx,
+                                                   yb0 + a.f0 + (a.f0 >= h1 ? 1 : 0) + dy, fb);
                         } else {
-                            int y1 = yb0 + a.f0 + (a.p0 ? 1 : 0);
-                            if (a.p0) tma2_load_3d(sa, &maps.part1, kc * TW_KCH, dx + a.p0, yb0 + a.f0 + dy, fb);
-                            if (a.f1) tma2_load_3d(sa + (size_t)(a.p0 ? a.W - a.p0 : 0) * 128, &maps.full1, kc * TW_KCH, dx, y1 + dy, fb);
+                            uint8_t *sf = sa + (size_t)(a.p0 ? a.W - a.p0 : 0) * 128;
+                            if (a.p0) tma2_load_3d(sa, &maps.part1, kc * TW_KCH, dx + a.p0, yb0 + a.f0 + (a.f0 >= h1 ? 1 : 0) + dy, fb);
+                            if (a.f1) {
+                                if (h1 <= r1s || h1 >= r1s + a.f1) {
+                                    tma2_load_3d(sf, &maps.full1, kc * TW_KCH, dx, yb0 + r1s + (r1s >= h1 ? 1 : 0) + dy, fb);
+                                } else {
+                                    tma2_load_3d(sf, &maps.fullh[h1 - r1s - 1], kc * TW_KCH, dx, yb0 + r1s + dy, fb);
+                                    tma2_load_3d(sf + (size_t)(h1 - r1s) * a.W * 128, &maps.fullh[r1s + a.f1 - h1 - 1], kc * TW_KCH, dx,
+                                                 yb0 + h1 + 1 + dy, fb);
+                                }
+                            }
                         }
                         tma2_load_2d(sb, &maps.w, kc * TW_KCH, a.w_row0 + tap * TW_C + (int)rank * 128, fb);
                         if (++stage == PR_STAGES) { stage = 0; phase ^= 1; }
@@ -194,8 +223,15 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
         int it = 0;
         for (int tile = pair; tile < a.n_tiles; tile += n_pairs, it++) {
             const int acc = it & 1;
-            const int yb = tile * a.RT + ry;
-            const bool valid = r < rows_total && yb < a.YB && (yb % a.rows_per_pos) != 0;
+            int yb = tile * a.RT + ry;
+            bool valid;
+            if (a.rr) {                                              // yb = real row -> padded row
+                valid = r < rows_total && yb < a.n_real;
+                int pos = yb / a.W;
+                yb += pos + 1;
+            } else {
+                valid = r < rows_total && yb < a.YB && (yb % a.rows_per_pos) != 0;
+            }
             const size_t gofs = ((size_t)yb * a.W + x) * TW_C;
             if (valid && a.skip) {                                   // idle until the MMAs finish: pull the skip row towards L2
 #pragma unroll

@@ -301,6 +301,7 @@ extern "C" int sgo_create(const sgo_config *cfg, sgo_engine **out)
     SGO_CUDA_OK(e, cudaMemset(e->leaf_count, 0, sizeof(int32_t) * e->G));
     SGO_CUDA_OK(e, cudaMemset(e->leaf_boards, 0, sizeof(Board) * GL));
     SGO_CUDA_OK(e, cudaMemset(e->meta, 0, sizeof(TreeMeta) * GT));
+    SGO_CUDA_OK(e, cudaMemset(e->root_p64, 0, sizeof(double) * SGO_APAD * GT));
     SGO_CUDA_OK(e, cudaMemset(e->wave, 0, sizeof(int32_t) * 8 * e->G));
     k_games_reset<<<warp_grid(e->G), WARPS_PER_BLOCK * 32>>>(e->boards, 0, e->G);
     SGO_CUDA_OK(e, cudaGetLastError());

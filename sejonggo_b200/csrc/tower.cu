@@ -44,6 +44,7 @@ struct sgo_tower {
     __nv_bfloat16 *stem_wb;                 // [C co][TW_STEM_K] bf16 stem weights, k = tap*17 + plane
     float *head_w4, *head_b4, *feat;        // fused 1x1 head convs: [C][4], [4]; features [max_pos][W*W][4]
     int f0, p0, f1;
+    int rr;                                 // real-row tiling (conv_pair.cuh): no MACs on pad rows; needs RT <= W and row runs <= PR_MAXH
     int32_t *err;
     int sm_count;
     // optional live profiling (bench.py roofline): 4 events per forward call
@@ -367,7 +368,22 @@ static int make_maps(sgo_engine *e, sgo_tower *t)
     t->f0 = 128 / t->W;
     t->p0 = 128 - t->f0 * t->W;
     t->f1 = t->RT - t->f0 - (t->p0 ? 1 : 0);
+    t->rr = (t->RT <= t->W && t->f0 <= PR_MAXH && t->f1 <= PR_MAXH && !getenv("SGO_TOWER_PADDED_TILES")) ? 1 : 0;
     t->pmaps = new PairMaps[4];
+    memset(t->pmaps, 0, sizeof(PairMaps) * 4);
+    for (int i = 0; i < 4 && t->rr; i++) {                  // one box map per row-run height, activations [0..2] and the stem im2col [3]
+        const int kw = i < 3 ? TW_C : TW_STEM_K;
+        cuuint64_t dims3[3] = {(cuuint64_t)kw, (cuuint64_t)t->W, (cuuint64_t)t->YB};
+        cuuint64_t str3[2] = {(cuuint64_t)kw * 2, (cuuint64_t)kw * 2 * t->W};
+        cuuint32_t es3[3] = {1, 1, 1};
+        for (int h = 1; h <= PR_MAXH; h++) {
+            cuuint32_t box3[3] = {TW_KCH, (cuuint32_t)t->W, (cuuint32_t)h};
+            CUresult rr = enc(&t->pmaps[i].fullh[h - 1], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, i < 3 ? (void *)t->act[i] : (void *)t->stem_col,
+                              dims3, str3, box3, es3, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (rr != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(row-run boxes) failed");
+        }
+    }
     for (int i = 0; i < 3; i++) {
         cuuint64_t dims3[3] = {(cuuint64_t)TW_C, (cuuint64_t)t->W, (cuuint64_t)t->YB};
         cuuint64_t str3[2] = {(cuuint64_t)TW_C * 2, (cuuint64_t)TW_C * 2 * t->W};
@@ -522,7 +538,8 @@ static int launch_conv(sgo_engine *e, sgo_tower *t, int n, int layer, int in, in
     PairArgs pa;
     pa.W = t->W; pa.RT = t->RT; pa.rows_per_pos = t->W + 1;
     pa.YB = n * (t->W + 1) + 1;
-    pa.n_tiles = (pa.YB + t->RT - 1) / t->RT;
+    pa.rr = t->rr; pa.n_real = n * t->W;
+    pa.n_tiles = t->rr ? (pa.n_real + t->RT - 1) / t->RT : (pa.YB + t->RT - 1) / t->RT;
     pa.relu = 1; pa.f0 = t->f0; pa.p0 = t->p0; pa.f1 = t->f1; pa.err = t->err;
     if (layer >= 0) {
         pa.n_taps = 9; pa.kchunks = TW_C / TW_KCH; pa.w_row0 = layer * 9 * TW_C;

@@ -39,7 +39,8 @@ def test_native_step_equals_composed_calls(mode, self_play, sym):
     for (ba, ma, pa), (bb, mb, pb) in zip(ta, tb):
         assert ma == mb
         assert ba.tobytes() == bb.tobytes()
-        assert np.array_equal(pa.view(np.uint64), pb.view(np.uint64))
+        if ma['root_f64']:                                   # the fp64 side array only means something at a noised root
+            assert np.array_equal(pa.view(np.uint64), pb.view(np.uint64))
 
 
 def test_records_pack_matches_fine_grained_exports():
