@@ -27,6 +27,7 @@ struct PairMaps {
     CUtensorMap full0, part0, part1, full1;   // activation boxes: (64, W, f0), (64, p0, 1), (64, W-p0, 1), (64, W, f1)
     CUtensorMap w;                            // weights box (64 ci, 128 co)
     CUtensorMap fullh[PR_MAXH];               // real-row tiling: (64, W, h) for h = 1..PR_MAXH (a run of rows inside ONE position)
+    CUtensorMap pf;                           // L2 prefetch box (C, W, pf_rows), unswizzled: half of the NEXT tile's input rows
 };
 
 struct PairArgs {
@@ -35,6 +36,9 @@ struct PairArgs {
     // is real row R = t*RT + i = (pos, y) at padded row pos*rows_per_pos + 1 + y; a tile crosses at most one position
     // boundary (needs RT <= W), so each CTA's full rows are one or two row runs.  n_real = positions * W.
     int rr, n_real;
+    int dbg;                  // timing ablations only (SGO_CONV_DEBUG): 1 = no epilogue global traffic, 2 = no A loads, 4 = no B loads,
+                              // 8 = tap-major k order (old), 16 = no next-tile L2 prefetch
+    int pf_rows;              // rows per prefetch box (0 = off): 2 * pf_rows >= RT + 3
     int n_taps, kchunks;      // 9 x 4 for the tower convs; 1 x 3 for the stem GEMM over the im2col tensor
     int f0, p0, f1;           // rank 0: f0 full rows + p0 pixels of row f0; rank 1: (W-p0) pixels of row f0 (if p0) + f1 full rows
     const float *bias;
@@ -80,6 +84,12 @@ __device__ __forceinline__ void tma2_load_2d(void *dst, const CUtensorMap *map, 
 {
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & PR_PEER_MASK), "r"(c0), "r"(c1) : "memory");
+}
+// bring a box into L2 only (no smem, no barrier): the next tile's activations, so that its first-touch DRAM reads do not all
+// land in the first k-blocks of the tile (every CTA reaches a tile boundary at about the same time)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
@@ -154,13 +164,36 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
                     yb0 = pos0 * a.rows_per_pos + 1 + y0;         // padded row of tile row 0; tile row i -> yb0 + i + (i >= h1)
                 }
                 const int r1s = a.f0 + (a.p0 ? 1 : 0);            // first full tile row of rank 1
-                for (int tap = 0; tap < a.n_taps && ok; tap++) {
+                if (a.pf_rows && !(a.dbg & 16) && tile + n_pairs < a.n_tiles) {
+                    int nyb = (tile + n_pairs) * a.RT;            // padded row of the next tile's row 0
+                    if (a.rr) nyb += nyb / a.W + 1;
+                    tma_prefetch_3d(&maps.pf, 0, 0, nyb - 1 + (int)rank * a.pf_rows);
+                }
+                const int nkb = a.n_taps * a.kchunks;
+                // k order: channel chunk outer, filter tap inner — the 9 taps of one chunk re-read (shifted) the same activation
+                // slice, so first-touch traffic is spread over the tile instead of filling its first 4 k-blocks
+                for (int kb = 0; kb < nkb && ok; kb++) {
+                    int tap, kc;
+                    if (a.dbg & 8) { tap = kb / a.kchunks; kc = kb - tap * a.kchunks; }
+                    else { kc = kb / a.n_taps; tap = kb - kc * a.n_taps; }
                     int dy = a.n_taps == 1 ? 0 : tap / 3 - 1, dx = a.n_taps == 1 ? 0 : tap % 3 - 1;
-                    for (int kc = 0; kc < a.kchunks; kc++) {
+                    {
                         ok = mbar_wait(&tail->empty[stage], phase ^ 1, a.err);
                         if (!ok) break;
                         uint8_t *sa = smem + (size_t)stage * PR_STAGE_BYTES, *sb = sa + PR_A_BYTES;
                         uint64_t *fb = &tail->full[stage];
+                        if (a.dbg & 6) {                                                  // ablation: drop operand loads
+                            if (rank == 0) mbar_expect_tx(fb, ((a.dbg & 2) ? 0u : a_bytes0 + a_bytes1) + ((a.dbg & 4) ? 0u : 2u * PR_B_BYTES));
+                            if (!(a.dbg & 4)) tma2_load_2d(sb, &maps.w, kc * TW_KCH, a.w_row0 + tap * TW_C + (int)rank * 128, fb);
+                            if (!(a.dbg & 2)) {
+                                if (rank == 0) { tma2_load_3d(sa, &maps.full0, kc * TW_KCH, dx, yb0 + dy, fb);
+                                                 if (a.p0) tma2_load_3d(sa + (size_t)a.f0 * a.W * 128, &maps.part0, kc * TW_KCH, dx, yb0 + a.f0 + dy, fb); }
+                                else { if (a.p0) tma2_load_3d(sa, &maps.part1, kc * TW_KCH, dx + a.p0, yb0 + a.f0 + dy, fb);
+                                       if (a.f1) tma2_load_3d(sa + (size_t)(a.p0 ? a.W - a.p0 : 0) * 128, &maps.full1, kc * TW_KCH, dx, yb0 + r1s + dy, fb); }
+                            }
+                            if (++stage == PR_STAGES) { stage = 0; phase ^= 1; }
+                            continue;
+                        }
                         if (rank == 0) {
                             mbar_expect_tx(fb, a_bytes0 + a_bytes1 + 2 * PR_B_BYTES);     // bytes of BOTH CTAs
                             if (h1 >= a.f0) {
@@ -233,6 +266,7 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
                 valid = r < rows_total && yb < a.YB && (yb % a.rows_per_pos) != 0;
             }
             const size_t gofs = ((size_t)yb * a.W + x) * TW_C;
+            if (a.dbg & 1) valid = false;                            // ablation: no epilogue global traffic
             if (valid && a.skip) {                                   // idle until the MMAs finish: pull the skip row towards L2
 #pragma unroll
                 for (int j = 0; j < 4; j++) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.skip + gofs + j * 64));

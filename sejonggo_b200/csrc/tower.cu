@@ -44,6 +44,7 @@ struct sgo_tower {
     __nv_bfloat16 *stem_wb;                 // [C co][TW_STEM_K] bf16 stem weights, k = tap*17 + plane
     float *head_w4, *head_b4, *feat;        // fused 1x1 head convs: [C][4], [4]; features [max_pos][W*W][4]
     int f0, p0, f1;
+    int pf_rows;                            // rows per next-tile L2 prefetch box
     int rr;                                 // real-row tiling (conv_pair.cuh): no MACs on pad rows; needs RT <= W and row runs <= PR_MAXH
     int32_t *err;
     int sm_count;
@@ -384,10 +385,18 @@ static int make_maps(sgo_engine *e, sgo_tower *t)
             if (rr != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(row-run boxes) failed");
         }
     }
+    t->pf_rows = (t->RT + 3 + 1) / 2;
     for (int i = 0; i < 3; i++) {
         cuuint64_t dims3[3] = {(cuuint64_t)TW_C, (cuuint64_t)t->W, (cuuint64_t)t->YB};
         cuuint64_t str3[2] = {(cuuint64_t)TW_C * 2, (cuuint64_t)TW_C * 2 * t->W};
         cuuint32_t es3[3] = {1, 1, 1};
+        {
+            cuuint32_t boxp[3] = {TW_C, (cuuint32_t)t->W, (cuuint32_t)t->pf_rows};
+            CUresult rp = enc(&t->pmaps[i].pf, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, t->act[i], dims3, str3, boxp, es3,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (rp != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(prefetch box) failed");
+        }
         struct { CUtensorMap *m; cuuint32_t bx, by; } boxes[4] = {
             {&t->pmaps[i].full0, (cuuint32_t)t->W, (cuuint32_t)t->f0},
             {&t->pmaps[i].part0, (cuuint32_t)(t->p0 ? t->p0 : 1), 1},
@@ -539,6 +548,8 @@ static int launch_conv(sgo_engine *e, sgo_tower *t, int n, int layer, int in, in
     pa.W = t->W; pa.RT = t->RT; pa.rows_per_pos = t->W + 1;
     pa.YB = n * (t->W + 1) + 1;
     pa.rr = t->rr; pa.n_real = n * t->W;
+    { const char *d = getenv("SGO_CONV_DEBUG"); pa.dbg = d ? atoi(d) : 0; }
+    pa.pf_rows = layer >= 0 ? t->pf_rows : 0;
     pa.n_tiles = t->rr ? (pa.n_real + t->RT - 1) / t->RT : (pa.YB + t->RT - 1) / t->RT;
     pa.relu = 1; pa.f0 = t->f0; pa.p0 = t->p0; pa.f1 = t->f1; pa.err = t->err;
     if (layer >= 0) {
