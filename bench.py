@@ -306,7 +306,7 @@ def run_ours(a):
                                                            a.blocks, a.sims, G, a.mode.upper()),
                     games_per_gpu=G, mode=a.mode, sims_per_ply=a.sims, moves_per_sec=r['plies'] / (r['ms'] * 1e-3),
                     l2="working set (trees %.1f GB, activations %.1f GB) >> 126 MB L2; no flush needed" %
-                       (G * bg.eng.T * 2 * arena * 6272 / 1e9, 3 * (a.max_positions * 18 + 1) * 17 * 512 / 1e9),
+                       (G * bg.eng.T * 2 * arena * 6272 / 1e9, 3 * (a.max_positions * 18 + 1) * 18 * 512 / 1e9),
                     step="one ply of every game", parallelism="games sharded, %d rank(s)" % world,
                     records_gathered=None if gathered is None else [int(g.numel()) for g in gathered]),
         e2e=dict(value=r2['sims'] / (r2['ms'] * 1e-3), unit="simulations/s", h2d_bytes_per_step=r2['h2d'] / a.steps,

@@ -160,7 +160,7 @@ int sgo_tower_check_sync(sgo_engine *e, int32_t slot, int32_t *h_flags, void *st
 int sgo_tower_profile(sgo_engine *e, int32_t slot, int32_t enable);
 int sgo_tower_profile_read_sync(sgo_engine *e, int32_t slot, double *h_out);
 /* test / profiling hooks: one tensor-core conv layer in isolation; raw activation buffers
- * bf16 [n*(S-1)+1][S-2][C] (row 0 and every (S-1)-th row are zero padding) */
+ * bf16 [n*(S-1)+1][S-1][C] (row 0 and every (S-1)-th row, and the last pixel of every row, are zero padding) */
 int sgo_tower_debug_conv(sgo_engine *e, int32_t slot, int32_t n, int32_t layer, int32_t in, int32_t out, int32_t skip, void *stream);
 int sgo_tower_act_copy(sgo_engine *e, int32_t slot, int32_t buf, int32_t n, void *d_data, int32_t to_tower, void *stream);
 

@@ -80,7 +80,9 @@ def load(build_if_needed=True):
     if _lib is not None:
         return _lib
     so = _build.SO
-    if build_if_needed:
+    if os.environ.get("SGO_LIBRARY"):                 # A/B runs against another build of the same ABI (tools/, profiles/)
+        so = os.environ["SGO_LIBRARY"]
+    elif build_if_needed:
         so = _build.build()
     if not os.path.isfile(so):
         raise RuntimeError("sejonggo_b200: CUDA library %s is missing — run `python -m sejonggo_b200._build`; "

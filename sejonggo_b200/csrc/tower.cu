@@ -11,12 +11,12 @@
 //          reach HBM); k_heads_fc does the dense policy (softmax) / value (tanh) layers
 //          (model.py:72-92) in fp32 with the "reverse" symmetry policy gather fused in.
 //
-// Activation layout in HBM: bf16 [YB][W][C], W = S-2 (Q11), YB = n_pos*(W+1)+1: every position
-// owns W pixel rows preceded by ONE all-zero pad row (shared top/bottom halo); left/right
-// halos come from TMA out-of-bounds zero fill.  A conv tile = RT consecutive rows (RT*W<=256),
-// so its 9 shifted A operands are plain 3-D TMA boxes at (c0, dx, yb0+dy).  (A dense 4-D
-// layout without pad rows was tried and is slower: more TMA boxes per k-block — see
-// profiles/r01_experiment_dense_*.json.)
+// Activation layout in HBM: bf16 [YB][P][C], W = S-2 (Q11), P = W+1, YB = n_pos*(W+1)+1: every position owns W pixel
+// rows preceded by ONE all-zero pad row and every row ends in ONE all-zero pad pixel, so the halo of any pixel is
+// at a fixed offset (q + dy*P + dx) in the flattened pixel index q = row*P + x and the conv is a shifted GEMM
+// (conv_pair.cuh).  History of the layout (profiles/): row tiles with per-tap TMA boxes (r01_tower_bench_pair*.json),
+// real-row tiles (r01_conv_real_row_tiling_ab.json) and a dense 4-D layout (r01_experiment_dense_*.json) all re-load
+// the A operand once per tap and are bound by L2->SM bytes.
 #include "engine.h"
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -31,21 +31,18 @@
 #define TW_STEM_K 192                      // 9 taps x 17 planes = 153, padded to 3 x 64
 
 struct sgo_tower {
-    int n_blocks, S, W, RT, max_pos, YB;
+    int n_blocks, S, W, P, max_pos, YB;      // P = W + 1 pixel pitch (one zero pad pixel per row); YB = padded rows
     int n_layers;
     float *stem_w, *stem_b;                 // [9][17][C], [C]
     __nv_bfloat16 *conv_w;                  // [n_layers][9][C co][C ci]
     float *conv_b;                          // [n_layers][C]
     float *pol_conv_w, *pol_conv_b, *pol_fc_w, *pol_fc_b;
     float *val_conv_w, *val_conv_b, *val_fc1_w, *val_fc1_b, *val_fc2_w, *val_fc2_b;
-    __nv_bfloat16 *act[3];                  // [YB][W][C]
-    struct PairMaps *pmaps;                 // [3] tensor maps of the CTA-pair kernel (conv_pair.cuh); [3] = stem im2col
-    __nv_bfloat16 *stem_col;                // [YB][W][TW_STEM_K] im2col of the input planes (0/1, +-1)
+    __nv_bfloat16 *act[3];                  // [YB*P][C]
+    struct PairMaps *pmaps;                 // [0..2] tensor maps of the CTA-pair kernel per activation buffer (conv_pair.cuh); [3] = stem im2col
+    __nv_bfloat16 *stem_col;                // [YB*P][TW_STEM_K] im2col of the input planes (0/1, +-1)
     __nv_bfloat16 *stem_wb;                 // [C co][TW_STEM_K] bf16 stem weights, k = tap*17 + plane
     float *head_w4, *head_b4, *feat;        // fused 1x1 head convs: [C][4], [4]; features [max_pos][W*W][4]
-    int f0, p0, f1;
-    int pf_rows;                            // rows per next-tile L2 prefetch box
-    int rr;                                 // real-row tiling (conv_pair.cuh): no MACs on pad rows; needs RT <= W and row runs <= PR_MAXH
     int32_t *err;
     int sm_count;
     // optional live profiling (bench.py roofline): 4 events per forward call
@@ -152,7 +149,7 @@ __device__ __forceinline__ void sym_src_t(int S, int sym, int y, int x, int &sy,
 // the packed bitboards: col[row(y), x][tap*17 + p] = plane p at (y+ky, x+kx)  (valid conv, Q11).
 // Every value is 0, 1 or +-1, exact in bf16.  One 16-B store per thread-item (8 k's).
 __global__ void __launch_bounds__(256)
-k_stem_im2col(const Board *boards, const int32_t *index, const int32_t *syms, int n, int S, __nv_bfloat16 *col)
+k_stem_im2col(const Board *boards, const int32_t *index, const int32_t *syms, int n, int S, __nv_bfloat16 *col /* [rows*(W+1)][TW_STEM_K] */)
 {
     __shared__ uint16_t cell[SGO_MAXS * SGO_MAXS];
     __shared__ int s_tm;
@@ -198,7 +195,7 @@ k_stem_im2col(const Board *boards, const int32_t *index, const int32_t *syms, in
             uint4 o;
             o.x = v[0] | ((uint32_t)v[1] << 16); o.y = v[2] | ((uint32_t)v[3] << 16);
             o.z = v[4] | ((uint32_t)v[5] << 16); o.w = v[6] | ((uint32_t)v[7] << 16);
-            *reinterpret_cast<uint4 *>(col + ((row0 + y) * W + x) * TW_STEM_K + k0) = o;
+            *reinterpret_cast<uint4 *>(col + ((row0 + y) * (W + 1) + x) * TW_STEM_K + k0) = o;
         }
     }
 }
@@ -362,82 +359,25 @@ static int make_maps(sgo_engine *e, sgo_tower *t)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return sgo_fail(e, "cuTensorMapEncodeTiled unavailable");
-    cuuint64_t dims[2] = {(cuuint64_t)TW_C, (cuuint64_t)(t->n_layers ? t->n_layers : 1) * 9 * TW_C};
-    cuuint64_t strides[1] = {(cuuint64_t)TW_C * 2};
     cuuint32_t es[2] = {1, 1};
-    // CTA-pair kernel: rank 0 = f0 full rows + p0 pixels, rank 1 = (W-p0) pixels + f1 full rows
-    t->f0 = 128 / t->W;
-    t->p0 = 128 - t->f0 * t->W;
-    t->f1 = t->RT - t->f0 - (t->p0 ? 1 : 0);
-    t->rr = (t->RT <= t->W && t->f0 <= PR_MAXH && t->f1 <= PR_MAXH && !getenv("SGO_TOWER_PADDED_TILES")) ? 1 : 0;
     t->pmaps = new PairMaps[4];
     memset(t->pmaps, 0, sizeof(PairMaps) * 4);
-    for (int i = 0; i < 4 && t->rr; i++) {                  // one box map per row-run height, activations [0..2] and the stem im2col [3]
-        const int kw = i < 3 ? TW_C : TW_STEM_K;
-        cuuint64_t dims3[3] = {(cuuint64_t)kw, (cuuint64_t)t->W, (cuuint64_t)t->YB};
-        cuuint64_t str3[2] = {(cuuint64_t)kw * 2, (cuuint64_t)kw * 2 * t->W};
-        cuuint32_t es3[3] = {1, 1, 1};
-        for (int h = 1; h <= PR_MAXH; h++) {
-            cuuint32_t box3[3] = {TW_KCH, (cuuint32_t)t->W, (cuuint32_t)h};
-            CUresult rr = enc(&t->pmaps[i].fullh[h - 1], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, i < 3 ? (void *)t->act[i] : (void *)t->stem_col,
-                              dims3, str3, box3, es3, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (rr != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(row-run boxes) failed");
-        }
-    }
-    t->pf_rows = (t->RT + 3 + 1) / 2;
-    for (int i = 0; i < 3; i++) {
-        cuuint64_t dims3[3] = {(cuuint64_t)TW_C, (cuuint64_t)t->W, (cuuint64_t)t->YB};
-        cuuint64_t str3[2] = {(cuuint64_t)TW_C * 2, (cuuint64_t)TW_C * 2 * t->W};
-        cuuint32_t es3[3] = {1, 1, 1};
-        {
-            cuuint32_t boxp[3] = {TW_C, (cuuint32_t)t->W, (cuuint32_t)t->pf_rows};
-            CUresult rp = enc(&t->pmaps[i].pf, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, t->act[i], dims3, str3, boxp, es3,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (rp != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(prefetch box) failed");
-        }
-        struct { CUtensorMap *m; cuuint32_t bx, by; } boxes[4] = {
-            {&t->pmaps[i].full0, (cuuint32_t)t->W, (cuuint32_t)t->f0},
-            {&t->pmaps[i].part0, (cuuint32_t)(t->p0 ? t->p0 : 1), 1},
-            {&t->pmaps[i].part1, (cuuint32_t)(t->p0 ? t->W - t->p0 : 1), 1},
-            {&t->pmaps[i].full1, (cuuint32_t)t->W, (cuuint32_t)(t->f1 ? t->f1 : 1)}};
-        for (int b = 0; b < 4; b++) {
-            cuuint32_t box3[3] = {TW_KCH, boxes[b].bx, boxes[b].by};
-            CUresult rr = enc(boxes[b].m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, t->act[i], dims3, str3, box3, es3,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (rr != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(pair activations) failed");
-        }
-        cuuint32_t boxw[2] = {TW_KCH, 128};
-        CUresult rr = enc(&t->pmaps[i].w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, t->conv_w, dims, strides, boxw, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    const cuuint64_t Q = (cuuint64_t)t->YB * t->P;
+    for (int i = 0; i < 4; i++) {                          // activation buffers [0..2], stem im2col [3]
+        const int kw = i < 3 ? TW_C : TW_STEM_K, halo = i < 3 ? t->P + 1 : 0;
+        cuuint64_t dims[2] = {(cuuint64_t)kw, Q};
+        cuuint64_t strides[1] = {(cuuint64_t)kw * 2};
+        cuuint32_t box[2] = {TW_KCH, (cuuint32_t)(128 + 2 * halo)};      // one CTA's 128 rows + the (dy, dx) halo on both sides
+        CUresult rr = enc(&t->pmaps[i].act, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, i < 3 ? (void *)t->act[i] : (void *)t->stem_col, dims, strides,
+                          box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (rr != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(pair weights) failed");
-    }
-    {   // stem GEMM: A = im2col tensor (K = TW_STEM_K), B = bf16 stem weights
-        cuuint64_t dims3[3] = {(cuuint64_t)TW_STEM_K, (cuuint64_t)t->W, (cuuint64_t)t->YB};
-        cuuint64_t str3[2] = {(cuuint64_t)TW_STEM_K * 2, (cuuint64_t)TW_STEM_K * 2 * t->W};
-        cuuint32_t es3[3] = {1, 1, 1};
-        struct { CUtensorMap *m; cuuint32_t bx, by; } boxes[4] = {
-            {&t->pmaps[3].full0, (cuuint32_t)t->W, (cuuint32_t)t->f0},
-            {&t->pmaps[3].part0, (cuuint32_t)(t->p0 ? t->p0 : 1), 1},
-            {&t->pmaps[3].part1, (cuuint32_t)(t->p0 ? t->W - t->p0 : 1), 1},
-            {&t->pmaps[3].full1, (cuuint32_t)t->W, (cuuint32_t)(t->f1 ? t->f1 : 1)}};
-        for (int b = 0; b < 4; b++) {
-            cuuint32_t box3[3] = {TW_KCH, boxes[b].bx, boxes[b].by};
-            CUresult rr = enc(boxes[b].m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, t->stem_col, dims3, str3, box3, es3,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (rr != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(stem im2col) failed");
-        }
-        cuuint64_t dw[2] = {(cuuint64_t)TW_STEM_K, (cuuint64_t)TW_C};
-        cuuint64_t sw_[1] = {(cuuint64_t)TW_STEM_K * 2};
+        if (rr != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(activation slab) failed");
+        cuuint64_t wdims[2] = {(cuuint64_t)kw, i < 3 ? (cuuint64_t)(t->n_layers ? t->n_layers : 1) * 9 * TW_C : (cuuint64_t)TW_C};
         cuuint32_t boxw[2] = {TW_KCH, 128};
-        CUresult rr = enc(&t->pmaps[3].w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, t->stem_wb, dw, sw_, boxw, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (rr != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(stem weights) failed");
+        rr = enc(&t->pmaps[i].w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, i < 3 ? (void *)t->conv_w : (void *)t->stem_wb, wdims, strides, boxw, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rr != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(weights) failed");
     }
     return 0;
 }
@@ -487,7 +427,8 @@ extern "C" int sgo_tower_load_weights(sgo_engine *e, int32_t slot, const sgo_tow
     memset(t, 0, sizeof(*t));
     e->tower[slot] = t;
     t->n_blocks = w->n_blocks; t->n_layers = 2 * w->n_blocks; t->S = e->S; t->W = e->S - 2;
-    t->RT = 256 / t->W; if (t->RT > 256) t->RT = 256;
+    t->P = t->W + 1;
+    if (t->P + 1 > PR_MAX_HALO) return sgo_fail(e, "board too wide for the conv slab");
     t->max_pos = max_positions;
     t->YB = max_positions * (t->W + 1) + 1;
     int P = t->W * t->W, A = e->A;
@@ -505,12 +446,12 @@ extern "C" int sgo_tower_load_weights(sgo_engine *e, int32_t slot, const sgo_tow
     DUP(t->val_fc1_b, w->val_fc1_b, 256, float);
     DUP(t->val_fc2_w, w->val_fc2_w, 256, float);
     DUP(t->val_fc2_b, w->val_fc2_b, 1, float);
-    size_t act_bytes = (size_t)t->YB * t->W * TW_C * sizeof(__nv_bfloat16);
+    size_t act_bytes = (size_t)t->YB * t->P * TW_C * sizeof(__nv_bfloat16);
     for (int i = 0; i < 3; i++) {
         SGO_CUDA_OK(e, cudaMalloc(&t->act[i], act_bytes));
-        SGO_CUDA_OK(e, cudaMemsetAsync(t->act[i], 0, act_bytes, S_(stream)));     // pad rows stay zero forever
+        SGO_CUDA_OK(e, cudaMemsetAsync(t->act[i], 0, act_bytes, S_(stream)));     // pad rows and pad pixels stay zero forever
     }
-    size_t col_bytes = (size_t)t->YB * t->W * TW_STEM_K * sizeof(__nv_bfloat16);
+    size_t col_bytes = (size_t)t->YB * t->P * TW_STEM_K * sizeof(__nv_bfloat16);
     SGO_CUDA_OK(e, cudaMalloc(&t->stem_col, col_bytes));
     SGO_CUDA_OK(e, cudaMemsetAsync(t->stem_col, 0, col_bytes, S_(stream)));
     SGO_CUDA_OK(e, cudaMalloc(&t->stem_wb, sizeof(__nv_bfloat16) * TW_C * TW_STEM_K));
@@ -545,18 +486,16 @@ extern "C" int sgo_tower_max_positions(sgo_engine *e, int32_t slot)
 static int launch_conv(sgo_engine *e, sgo_tower *t, int n, int layer, int in, int out, int skip, void *stream, bool heads = false)
 {
     PairArgs pa;
-    pa.W = t->W; pa.RT = t->RT; pa.rows_per_pos = t->W + 1;
+    pa.W = t->W; pa.P = t->P; pa.rows_per_pos = t->W + 1;
     pa.YB = n * (t->W + 1) + 1;
-    pa.rr = t->rr; pa.n_real = n * t->W;
     { const char *d = getenv("SGO_CONV_DEBUG"); pa.dbg = d ? atoi(d) : 0; }
-    pa.pf_rows = layer >= 0 ? t->pf_rows : 0;
-    pa.n_tiles = t->rr ? (pa.n_real + t->RT - 1) / t->RT : (pa.YB + t->RT - 1) / t->RT;
-    pa.relu = 1; pa.f0 = t->f0; pa.p0 = t->p0; pa.f1 = t->f1; pa.err = t->err;
+    pa.n_tiles = (pa.YB * t->P + 255) / 256;
+    pa.relu = 1; pa.err = t->err;
     if (layer >= 0) {
-        pa.n_taps = 9; pa.kchunks = TW_C / TW_KCH; pa.w_row0 = layer * 9 * TW_C;
+        pa.n_taps = 9; pa.kchunks = TW_C / TW_KCH; pa.w_row0 = layer * 9 * TW_C; pa.halo = t->P + 1;
         pa.bias = t->conv_b + (size_t)layer * TW_C;
     } else {
-        pa.n_taps = 1; pa.kchunks = TW_STEM_K / TW_KCH; pa.w_row0 = 0;
+        pa.n_taps = 1; pa.kchunks = TW_STEM_K / TW_KCH; pa.w_row0 = 0; pa.halo = 0;
         pa.bias = t->stem_b;
     }
     pa.skip = skip >= 0 ? t->act[skip] : nullptr;
@@ -676,13 +615,13 @@ extern "C" int sgo_tower_debug_conv(sgo_engine *e, int32_t slot, int32_t n, int3
     return launch_conv(e, t, n, layer, in, out, skip, stream);
 }
 
-// raw activation buffer access (bf16 [n*(W+1)+1][W][C]) for tests
+// raw activation buffer access (bf16 [n*(W+1)+1][W+1][C]) for tests
 extern "C" int sgo_tower_act_copy(sgo_engine *e, int32_t slot, int32_t buf, int32_t n, void *d_data, int32_t to_tower, void *stream)
 {
     if (slot < 0 || slot > 1 || !e->tower[slot]) return sgo_fail(e, "tower slot has no weights");
     sgo_tower *t = e->tower[slot];
     if (buf < 0 || buf > 2 || n < 1 || n > t->max_pos) return sgo_fail(e, "act_copy arguments out of range");
-    size_t bytes = ((size_t)n * (t->W + 1) + 1) * t->W * TW_C * sizeof(__nv_bfloat16);
+    size_t bytes = ((size_t)n * (t->W + 1) + 1) * t->P * TW_C * sizeof(__nv_bfloat16);
     if (to_tower) SGO_CUDA_OK(e, cudaMemcpyAsync(t->act[buf], d_data, bytes, cudaMemcpyDeviceToDevice, S_(stream)));
     else SGO_CUDA_OK(e, cudaMemcpyAsync(d_data, t->act[buf], bytes, cudaMemcpyDeviceToDevice, S_(stream)));
     return 0;

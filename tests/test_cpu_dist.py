@@ -38,9 +38,13 @@ WORKER = textwrap.dedent('''
 def test_world2_gloo(tmp_path):
     script = tmp_path / "w.py"
     script.write_text(WORKER % ROOT)
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29731")
+    import socket
+    with socket.socket() as sk:                      # a free port: a fixed one can still be in TIME_WAIT from the last run
+        sk.bind(("127.0.0.1", 0))
+        port = str(sk.getsockname()[1])
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
+                        "--master-addr", "127.0.0.1", "--master-port", port, str(script)],
                        env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-3000:]
     assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout

@@ -18,9 +18,8 @@ def main():
     m = model.TowerModel("v", size=S, n_blocks=1, seed=0, max_positions=n)
     m.attach(e, 0)
     out = {}
-    for name, dbg, skip in (("full+skip", 0, 2), ("tap_major", 8, 2), ("no_prefetch", 16, 2), ("tap_major_no_prefetch (old)", 24, 2),
-                            ("full+skip again", 0, 2), ("full", 0, -1), ("noEpi", 1, 2), ("noA", 2, 2), ("noB", 4, 2), ("noAB", 6, 2),
-                            ("noAB_noEpi", 7, 2), ("old again", 24, 2), ("full+skip 3", 0, 2)):
+    for name, dbg, skip in (("full+skip", 0, 2), ("full", 0, -1), ("noEpi", 1, 2), ("noA", 2, 2), ("noB", 4, 2), ("noAB", 6, 2),
+                            ("noAB_noEpi", 7, 2), ("full+skip again", 0, 2)):
         os.environ["SGO_CONV_DEBUG"] = str(dbg)
         fn = lambda: e._ck(e.lib.sgo_tower_debug_conv(e.h, 0, n, 1, 0, 1, skip, e._stream()))
         for _ in range(3):
