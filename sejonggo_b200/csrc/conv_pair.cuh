@@ -37,7 +37,8 @@ struct PairMaps {
 struct PairArgs {
     int W, P, rows_per_pos, YB, n_tiles, w_row0, relu;
     int n_taps, kchunks, halo;                // 9 x 4, halo P+1 for the tower convs; 1 x 3, halo 0 for the stem GEMM over the im2col tensor
-    int dbg;                                  // timing ablations only (SGO_CONV_DEBUG): 1 = no epilogue global traffic, 2 = no A loads, 4 = no B loads
+    int dbg;                                  // timing ablations only (SGO_CONV_DEBUG): 1 = no epilogue global traffic, 2 = no A loads, 4 = no B loads,
+                                              // 32 = no activation stores, 64 = no skip loads
     const float *bias;
     const __nv_bfloat16 *skip;
     __nv_bfloat16 *out;                       // nullptr: do not store the activations (last layer feeding only the heads)
@@ -83,6 +84,22 @@ __device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t adesc, uint
                  "setp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// the same with the two 64-bit smem descriptors given as (low word, shared high word)
+__device__ __forceinline__ void umma2_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+                 "mov.b64 da, {%1, %3};\n\t"
+                 "mov.b64 db, {%2, %3};\n\t"
+                 "setp.ne.b32 p, %5, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 // arrive on the barrier at this smem offset in BOTH CTAs once the pair's MMAs so far retire
 __device__ __forceinline__ void umma2_commit_mc(uint64_t *bar)
@@ -135,8 +152,10 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
     const uint32_t tmem_base = tail->tmem_base;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
             // ---- producer: one A slab per channel chunk, one weight block per (chunk, tap) -------------------------
+            // (whole warp in the control flow, one elected lane issues: see the MMA issuer below)
+            const bool leader = elect_one();
             uint32_t slab = 0, sphase = 0, stage = 0, phase = 0;
             const uint32_t slab_bytes = (uint32_t)(128 + 2 * a.halo) * 128u;
             const bool no_a = a.dbg & 2, no_b = a.dbg & 4;
@@ -146,52 +165,70 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
                 for (int kc = 0; kc < a.kchunks && ok; kc++) {
                     ok = mbar_wait(&tail->a_empty[slab], sphase ^ 1, a.err);
                     if (!ok) break;
-                    if (rank == 0) mbar_expect_tx(&tail->a_full[slab], no_a ? 0u : 2u * slab_bytes);     // bytes of BOTH CTAs
-                    if (!no_a) tma2_load_2d(smem + (size_t)slab * PR_SLAB_BYTES, &maps.act, kc * TW_KCH, q_lo, &tail->a_full[slab]);
+                    if (leader) {
+                        if (rank == 0) mbar_expect_tx(&tail->a_full[slab], no_a ? 0u : 2u * slab_bytes);  // bytes of BOTH CTAs
+                        if (!no_a) tma2_load_2d(smem + (size_t)slab * PR_SLAB_BYTES, &maps.act, kc * TW_KCH, q_lo, &tail->a_full[slab]);
+                    }
                     if (++slab == PR_SLABS) { slab = 0; sphase ^= 1; }
                     for (int tap = 0; tap < a.n_taps; tap++) {
                         ok = mbar_wait(&tail->b_empty[stage], phase ^ 1, a.err);
                         if (!ok) break;
-                        if (rank == 0) mbar_expect_tx(&tail->b_full[stage], no_b ? 0u : 2u * PR_B_BYTES);
-                        if (!no_b) tma2_load_2d(smem_b + (size_t)stage * PR_B_BYTES, &maps.w, kc * TW_KCH,
-                                                a.w_row0 + tap * TW_C + (int)rank * 128, &tail->b_full[stage]);
+                        if (leader) {
+                            if (rank == 0) mbar_expect_tx(&tail->b_full[stage], no_b ? 0u : 2u * PR_B_BYTES);
+                            if (!no_b) tma2_load_2d(smem_b + (size_t)stage * PR_B_BYTES, &maps.w, kc * TW_KCH,
+                                                    a.w_row0 + tap * TW_C + (int)rank * 128, &tail->b_full[stage]);
+                        }
                         if (++stage == PR_BSTAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (rank == 0 && lane == 0) {
+        if (rank == 0) {
             // ---- MMA issuer: 9 taps x 4 K-steps on one slab, descriptor start shifted by (dy*P + dx) rows ------------
+            // The WHOLE warp runs the (warp-uniform) control flow and the barrier waits; one elected lane issues.  Written
+            // this way — and with the descriptors kept as a constant high word plus a running 32-bit low word — the loop
+            // is ~45 SASS instructions per k-block instead of ~130 (a lane==0 branch makes nvcc wrap every tcgen05
+            // instruction in an ELECT/R2UR.BROADCAST waterfall loop); at ~130 the single issuing thread needed about as
+            // long as the 512 tensor cycles of the k-block itself (ncu: pipe 73% active with no barrier stalls).
+            const bool leader = elect_one();
             uint32_t slab = 0, sphase = 0, stage = 0, phase = 0;
+            const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);       // SBO 1024 B, version 1, SWIZZLE_128B
+            const uint32_t a_lo0 = ((smem_u32(smem) & 0x3FFFF) >> 4) | (1u << 16);          // + slab * (PR_SLAB_BYTES >> 4)
+            const uint32_t b_lo0 = ((smem_u32(smem_b) & 0x3FFFF) >> 4) | (1u << 16);        // + stage * (PR_B_BYTES >> 4)
             bool ok = true;
             int it = 0;
             for (int tile = pair; tile < a.n_tiles && ok; tile += n_pairs, it++) {
-                const int acc = it & 1;
-                ok = mbar_wait(&tail->tmem_empty[acc], ((it >> 1) & 1) ^ 1, a.err);    // both epilogues drained this stage
+                const uint32_t d_tmem = tmem_base + (uint32_t)(it & 1) * 256u;
+                ok = mbar_wait(&tail->tmem_empty[it & 1], ((it >> 1) & 1) ^ 1, a.err);  // both epilogues drained this stage
                 if (!ok) break;
                 tc_fence_after();
+                uint32_t accum = 0;
                 for (int kc = 0; kc < a.kchunks && ok; kc++) {
                     ok = mbar_wait(&tail->a_full[slab], sphase, a.err);
                     if (!ok) break;
-                    const uint32_t sa = smem_u32(smem + (size_t)slab * PR_SLAB_BYTES);
+                    const uint32_t a_lo = a_lo0 + slab * (PR_SLAB_BYTES >> 4) + (uint32_t)a.halo * 8u;
                     for (int tap = 0; tap < a.n_taps; tap++) {
                         ok = mbar_wait(&tail->b_full[stage], phase, a.err);
                         if (!ok) break;
                         tc_fence_after();
                         const int shift = a.n_taps == 1 ? 0 : (tap / 3 - 1) * a.P + (tap % 3 - 1);
-                        const uint32_t a0 = sa + (uint32_t)(a.halo + shift) * 128u, sb = smem_u32(smem_b + (size_t)stage * PR_B_BYTES);
+                        const uint32_t alo = a_lo + (uint32_t)(shift * 8), blo = b_lo0 + stage * (PR_B_BYTES >> 4);
+                        if (leader) {
 #pragma unroll
-                        for (int k = 0; k < TW_KCH / 16; k++)
-                            umma2_bf16(tmem_base + acc * 256, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(sb + k * 32), PR_IDESC,
-                                       (kc | tap | k) ? 1u : 0u);
-                        umma2_commit_mc(&tail->b_empty[stage]);                         // frees the weight slot in both CTAs
+                            for (int k = 0; k < TW_KCH / 16; k++) {
+                                umma2_bf16_lohi(d_tmem, alo + 2 * k, blo + 2 * k, desc_hi, PR_IDESC, accum);
+                                accum = 1;
+                            }
+                            umma2_commit_mc(&tail->b_empty[stage]);                     // frees the weight slot in both CTAs
+                        }
+                        accum = 1;
                         if (++stage == PR_BSTAGES) { stage = 0; phase ^= 1; }
                     }
-                    if (ok) umma2_commit_mc(&tail->a_empty[slab]);                      // frees the slab in both CTAs
+                    if (ok && leader) umma2_commit_mc(&tail->a_empty[slab]);            // frees the slab in both CTAs
                     if (++slab == PR_SLABS) { slab = 0; sphase ^= 1; }
                 }
-                if (ok) umma2_commit_mc(&tail->tmem_full[acc]);
+                if (ok && leader) umma2_commit_mc(&tail->tmem_full[it & 1]);
             }
         }
     } else {
@@ -219,7 +256,7 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
 #pragma unroll 1
             for (int c = 0; c < TW_C / 32; c++) {
                 uint4 sk[4];
-                if (valid && a.skip) {
+                if (valid && a.skip && !(a.dbg & 64)) {
                     const uint4 *sp = reinterpret_cast<const uint4 *>(a.skip + gofs + c * 32);
 #pragma unroll
                     for (int j = 0; j < 4; j++) sk[j] = sp[j];
@@ -248,7 +285,7 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
                             h0 = fmaf(f1, wb.x, h0); h1 = fmaf(f1, wb.y, h1); h2 = fmaf(f1, wb.z, h2); h3 = fmaf(f1, wb.w, h3);
                         }
                     }
-                    if (a.out) {
+                    if (a.out && !(a.dbg & 32)) {
                         uint4 *op = reinterpret_cast<uint4 *>(a.out + gofs + c * 32);
 #pragma unroll
                         for (int j = 0; j < 4; j++) op[j] = o[j];

@@ -64,7 +64,7 @@ def broadcast_params(params, src=0, device=None):
 
 def gather_records(payload, dst=0, device=None):
     """payload: 1-D uint8 tensor of this rank's packed records.  Two-phase gather: byte counts
-    (all_gather), then the padded payloads.  Returns a list of per-rank tensors on dst, else None."""
+    (all_gather), then a gather of the padded payloads to dst.  Returns a list of per-rank tensors on dst, else None."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return [payload]
     world, rank = dist.get_world_size(), dist.get_rank()
@@ -75,8 +75,8 @@ def gather_records(payload, dst=0, device=None):
     mx = int(max(int(c.item()) for c in counts))
     buf = torch.zeros(mx, dtype=torch.uint8, device=dev)
     buf[:payload.numel()] = payload.to(dev)
-    bufs = [torch.zeros(mx, dtype=torch.uint8, device=dev) for _ in range(world)]
-    dist.all_gather(bufs, buf)
+    bufs = [torch.zeros(mx, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == dst else None
+    dist.gather(buf, gather_list=bufs, dst=dst)          # payloads travel to dst only (NCCL: grouped send/recv)
     if rank != dst:
         return None
     return [b[:int(c.item())].cpu() for b, c in zip(bufs, counts)]

@@ -19,7 +19,7 @@ def main():
     m.attach(e, 0)
     out = {}
     for name, dbg, skip in (("full+skip", 0, 2), ("full", 0, -1), ("noEpi", 1, 2), ("noA", 2, 2), ("noB", 4, 2), ("noAB", 6, 2),
-                            ("noAB_noEpi", 7, 2), ("full+skip again", 0, 2)):
+                            ("noAB_noEpi", 7, 2), ("noStore", 32, 2), ("noSkipLoad", 64, 2), ("noStore_noSkipLoad", 96, 2), ("full+skip again", 0, 2)):
         os.environ["SGO_CONV_DEBUG"] = str(dbg)
         fn = lambda: e._ck(e.lib.sgo_tower_debug_conv(e.h, 0, n, 1, 0, 1, skip, e._stream()))
         for _ in range(3):
