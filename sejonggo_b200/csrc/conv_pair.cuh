@@ -23,6 +23,9 @@
 //   k order: channel chunk outer (one A slab), filter tap inner (nine 64x256 weight blocks through an 8-stage ring).
 #pragma once
 
+#ifndef PR_WIDE_LDST
+#define PR_WIDE_LDST 1                  // 256-bit epilogue loads/stores (one full 32-B sector per lane per instruction): +2% on the convs
+#endif
 #define PR_SLABS 3
 #define PR_SLAB_BYTES (21 * 1024)                  // >= (128 + 2 * (P + 1)) * 128 for P <= 18
 #define PR_BSTAGES 8
@@ -253,26 +256,31 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
             if (!ok) break;
             tc_fence_after();
             float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
+            const uint32_t t_addr = tmem_base + ((uint32_t)(qw * 32) << 16) + acc * 256;
 #pragma unroll 1
-            for (int c = 0; c < TW_C / 32; c++) {
-                uint4 sk[4];
-                if (valid && a.skip && !(a.dbg & 64)) {
+            for (int c = 0; c < TW_C / 32; c++) {                    // (software-pipelining the TMEM loads over a fully
+                uint32_t sk[16];                                     //  unrolled loop was measured slower: profiles/r01_conv_epilogue_ab.json)
+                const bool do_skip = valid && a.skip && !(a.dbg & 64);
+                if (do_skip) {
+#if PR_WIDE_LDST
+                    ldg256(a.skip + gofs + c * 32, sk);
+                    ldg256(a.skip + gofs + c * 32 + 16, sk + 8);
+#else
                     const uint4 *sp = reinterpret_cast<const uint4 *>(a.skip + gofs + c * 32);
 #pragma unroll
-                    for (int j = 0; j < 4; j++) sk[j] = sp[j];
+                    for (int j = 0; j < 4; j++) reinterpret_cast<uint4 *>(sk)[j] = sp[j];
+#endif
                 }
                 uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(qw * 32) << 16) + acc * 256 + c * 32, v);
+                tmem_ld32(t_addr + c * 32, v);
                 if (valid) {
-                    uint4 o[4];
-                    uint32_t *ow = reinterpret_cast<uint32_t *>(o);
-                    const uint32_t *sw = reinterpret_cast<const uint32_t *>(sk);
+                    uint32_t ow[16];
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
                         float f0 = __uint_as_float(v[2 * j]) + tail->bias[c * 32 + 2 * j];
                         float f1 = __uint_as_float(v[2 * j + 1]) + tail->bias[c * 32 + 2 * j + 1];
                         if (a.skip) {
-                            __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162 *>(&sw[j]);
+                            __nv_bfloat162 s2 = *reinterpret_cast<const __nv_bfloat162 *>(&sk[j]);
                             f0 += __bfloat162float(s2.x);
                             f1 += __bfloat162float(s2.y);
                         }
@@ -286,9 +294,14 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
                         }
                     }
                     if (a.out && !(a.dbg & 32)) {
+#if PR_WIDE_LDST
+                        stg256(a.out + gofs + c * 32, ow);
+                        stg256(a.out + gofs + c * 32 + 16, ow + 8);
+#else
                         uint4 *op = reinterpret_cast<uint4 *>(a.out + gofs + c * 32);
 #pragma unroll
-                        for (int j = 0; j < 4; j++) op[j] = o[j];
+                        for (int j = 0; j < 4; j++) op[j] = reinterpret_cast<const uint4 *>(ow)[j];
+#endif
                     }
                 }
             }
