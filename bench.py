@@ -148,6 +148,7 @@ def cpu_tower_selfplay(mode, blocks, warm, steps):
     import numpy as np
     import torch
     from oracle import oracle as o, game_loop as gl
+    torch.set_num_threads(os.cpu_count() or 1)       # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host thread
     m = _CpuTower(blocks)
     board, _ = o.game_init(SIZE)
     p, _ = m.predict_on_batch(board)
