@@ -48,16 +48,30 @@ def evaluate(boards, salt=0, sharp=False):
     return policy.astype(np.float32), value.astype(np.float32)
 
 
+def evaluate_uniform(boards):
+    """SURVEY §8d config 1 (BASELINE.json configs[0]): policy 1/(S*S+1) float32, value 0.0 — the
+    reference's no-network CPU case; every PUCT score ties, so it is the tie-break stress test."""
+    b = np.asarray(boards)
+    n, S = b.shape[0], b.shape[1]
+    A = S * S + 1
+    return np.full((n, A), np.float32(1.0) / np.float32(A), np.float32), np.zeros(n, np.float32)
+
+
+def evaluate_kind(boards, salt=0, sharp=False, kind="fake"):
+    return evaluate_uniform(boards) if kind == "uniform" else evaluate(boards, salt, sharp)
+
+
 class FakeModel(object):
     """predict_on_batch-compatible wrapper (self_play.py:70,187 protocol)."""
 
-    def __init__(self, name="fake_model", salt=0, sharp=False):
+    def __init__(self, name="fake_model", salt=0, sharp=False, kind="fake"):
         self.name = name
         self.salt = salt
         self.sharp = sharp
+        self.kind = kind
         self.calls = []
 
     def predict_on_batch(self, X):
-        p, v = evaluate(X, self.salt, self.sharp)
+        p, v = evaluate_kind(X, self.salt, self.sharp, self.kind)
         self.calls.append(np.asarray(X).shape[0])
         return p, v.reshape(-1, 1)

@@ -169,11 +169,11 @@ def gen_mcts(size, mode, batch, steps, plies, seed, tag):
 
 
 # --------------------------------------------------------------- game loop
-def gen_game(size, mode, batch, sims, stop_exploration, self_play, num_moves, seed, tag, resign=None):
+def gen_game(size, mode, batch, sims, stop_exploration, self_play, num_moves, seed, tag, resign=None, evalkind="fake"):
     """Full play_game / play_game_async run with recorded RNG draws."""
     import numpy as np, random
     ns = _setup(size, overrides={'ENERGY': batch, 'MCTS_BATCH_SIZE': batch, 'MCTS_SIMULATIONS': sims})
-    from oracle.fake_eval import evaluate, FakeModel
+    from oracle.fake_eval import evaluate_kind, FakeModel
     from oracle import oracle as o
     ns.symmetry.SYMMETRIES = ns.symmetry.SYMMETRIES[0:1]
     play = ns.play
@@ -204,8 +204,8 @@ def gen_game(size, mode, batch, sims, stop_exploration, self_play, num_moves, se
 
     _play_mod.random = coin
     _play_mod.np.random.dirichlet = dirichlet
-    m1 = FakeModel("model_1", salt=seed, sharp=True)
-    m2 = FakeModel("model_2", salt=seed + 1, sharp=True)
+    m1 = FakeModel("model_1", salt=seed, sharp=True, kind=evalkind)
+    m2 = FakeModel("model_2", salt=seed + 1, sharp=True, kind=evalkind)
     if mode == 'a':
         ns.self_play.np.random.choice = choice
         if self_play:
@@ -217,7 +217,7 @@ def gen_game(size, mode, batch, sims, stop_exploration, self_play, num_moves, se
         ns.nomodel_self_play.np.random.choice = choice
         salts = {"BEST_SYM": seed, "LATEST_SYM": seed + 1, "BEST": seed, "LATEST": seed + 1}
         ns.names = {"BEST_SYM": "model_1", "LATEST_SYM": "model_2", "BEST": "model_1", "LATEST": "model_2"}
-        ns.evaluator = lambda ind, board: (lambda p, v: (p[0], v[0]))(*evaluate(board, salts[ind], True))
+        ns.evaluator = lambda ind, board: (lambda p, v: (p[0], v[0]))(*evaluate_kind(board, salts[ind], True, evalkind))
         i1, i2 = ("BEST_SYM", "BEST_SYM") if self_play else ("BEST_SYM", "LATEST_SYM")
         gd = ns.nomodel_self_play.play_game_async(i1, i2, batch, stop_exploration, 0, self_play=self_play,
                                                   num_moves=num_moves, resign_model1=resign, resign_model2=resign)
@@ -226,7 +226,7 @@ def gen_game(size, mode, batch, sims, stop_exploration, self_play, num_moves, se
     np.savez_compressed(
         os.path.join(OUT, "game_%s.npz" % tag), size=size, mode=mode, batch=batch, sims=sims,
         stop_exploration=stop_exploration, self_play=int(self_play), num_moves=-1 if num_moves is None else num_moves,
-        seed=seed, resign=np.nan if resign is None else resign,
+        seed=seed, resign=np.nan if resign is None else resign, evalkind=evalkind,
         choice=np.array(rec['choice'], np.int32), noise=np.array(rec['noise'], np.float64).reshape(-1, A),
         coin=np.array(rec['coin'], np.float64),
         boards=np.array([o.pack_board(np.ascontiguousarray(m['board'], dtype=np.int32)) for m in mv], np.uint32),
@@ -257,6 +257,9 @@ JOBS = [
     ("game", dict(size=9, mode='b', batch=8, sims=32, stop_exploration=6, self_play=True, num_moves=14, seed=14, tag="b_selfplay_s9")),
     ("game", dict(size=9, mode='b', batch=8, sims=32, stop_exploration=0, self_play=False, num_moves=10, seed=15, tag="b_eval_s9")),
     ("game", dict(size=9, mode='a', batch=8, sims=16, stop_exploration=3, self_play=True, num_moves=None, seed=16, tag="a_resign_s9", resign=0.5)),
+    # BASELINE.json configs[0] / SURVEY §8d config 1: 9x9, 64 sims/ply, uniform evaluator, seed 0, 30 plies, modes A and B
+    ("game", dict(size=9, mode='a', batch=8, sims=64, stop_exploration=30, self_play=True, num_moves=30, seed=0, tag="a_config1_s9", evalkind="uniform")),
+    ("game", dict(size=9, mode='b', batch=8, sims=64, stop_exploration=30, self_play=True, num_moves=30, seed=0, tag="b_config1_s9", evalkind="uniform")),
 ]
 
 if __name__ == "__main__":

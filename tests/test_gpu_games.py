@@ -24,8 +24,9 @@ def test_game_fixture(name):
     S, mode, batch, sims, seed = int(z["size"]), str(z["mode"]), int(z["batch"]), int(z["sims"]), int(z["seed"])
     kw = game_kwargs(z)
     rng = gl.ReplayRng(coin=z["coin"], noise=z["noise"], choice=z["choice"])
-    m1 = FakeModel("model_1", salt=seed, sharp=True)
-    m2 = m1 if kw['self_play'] else FakeModel("model_2", salt=seed + 1, sharp=True)
+    kind = str(z["evalkind"]) if "evalkind" in z.files else "fake"
+    m1 = FakeModel("model_1", salt=seed, sharp=True, kind=kind)
+    m2 = m1 if kw['self_play'] else FakeModel("model_2", salt=seed + 1, sharp=True, kind=kind)
     old = dict(conf)
     try:
         conf.update(SIZE=S, MCTS_BATCH_SIZE=batch, ENERGY=batch, MCTS_SIMULATIONS=sims, KOMI=5.5)

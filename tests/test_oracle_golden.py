@@ -7,7 +7,7 @@ import pytest
 
 from oracle import oracle as o
 from oracle import game_loop as gl
-from oracle.fake_eval import evaluate, FakeModel
+from oracle.fake_eval import evaluate, evaluate_kind, FakeModel
 from tests.treeio import oracle_rows, rows_equal
 from tests.conftest import GOLDEN
 
@@ -108,9 +108,10 @@ def test_game_fixture(name):
     S, mode, batch, sims, seed = int(z["size"]), str(z["mode"]), int(z["batch"]), int(z["sims"]), int(z["seed"])
     rng = gl.ReplayRng(coin=z["coin"], noise=z["noise"], choice=z["choice"])
     kw = game_kwargs(z)
+    kind = str(z["evalkind"]) if "evalkind" in z.files else "fake"
     if mode == 'a':
-        m1 = FakeModel("model_1", salt=seed, sharp=True)
-        m2 = m1 if kw['self_play'] else FakeModel("model_2", salt=seed + 1, sharp=True)
+        m1 = FakeModel("model_1", salt=seed, sharp=True, kind=kind)
+        m2 = m1 if kw['self_play'] else FakeModel("model_2", salt=seed + 1, sharp=True, kind=kind)
         gd = gl.play_game(m1, m2, sims, size=S, mcts_batch_size=batch, rng=rng, **kw)
         calls = m1.calls + [-1] + (m2.calls if m2 is not m1 else [])
         assert calls == list(z["calls"])
@@ -119,7 +120,7 @@ def test_game_fixture(name):
         names = {"BEST_SYM": "model_1", "LATEST_SYM": "model_2"}
 
         def predict(tag, board, sym):
-            p, v = evaluate(board, salts[tag], True)
+            p, v = evaluate_kind(board, salts[tag], True, kind)
             return p[0], v[0]
 
         i1, i2 = ("BEST_SYM", "BEST_SYM") if kw['self_play'] else ("BEST_SYM", "LATEST_SYM")
