@@ -171,10 +171,13 @@ int sgo_tower_act_copy(sgo_engine *e, int32_t slot, int32_t buf, int32_t n, void
  *          (= ENERGY) busy-flag selections, evaluation, expand, resumed while any game reports
  *          "No best leaf", then the FIFO back-propagation of `total_energy` results.
  * Leaves are evaluated by the network slot d_model_of_game[g] (NULL = slot 0 for every game)
- * with symmetry ids d_sym_game[g] (symmetry.random_symmetry_predict, one draw per game per
- * batch; NULL = identity).  *h_leaves_done = simulations performed (synchronises). */
+ * with symmetry ids (symmetry.random_symmetry_predict; NULL = identity): d_sym[g], one draw per game
+ * per batch as in mode A (self_play.py:70), or with sym_per_leaf != 0 d_sym[g*max_leaves + l], one draw
+ * per predict request as in mode B (predicting_queue_worker.py:88-92).
+ * *h_leaves_done = simulations performed (synchronises). */
 int sgo_selfplay_step(sgo_engine *e, int32_t mode, const int32_t *d_tree_sel, const int32_t *d_model_of_game,
-                      int32_t leaves, int32_t total_energy, const int32_t *d_sym_game, int32_t *h_leaves_done, void *stream);
+                      int32_t leaves, int32_t total_energy, const int32_t *d_sym, int32_t sym_per_leaf,
+                      int32_t *h_leaves_done, void *stream);
 /* self_play.py:203-214 move_data for every game, packed: uint32 [G][sgo_record_words()] =
  * board (16 x ceil(S*S/32) plane words + to_move), move index, value (f32 bits), tree-valid
  * flag, policy_target = root priors as f32 [S*S+1] (Q14).  d_moves / d_values may be NULL. */

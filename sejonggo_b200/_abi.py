@@ -57,7 +57,7 @@ _PROTOS = {
     "sgo_tower_load_weights": [vp, i32, vp, i32, vp],
     "sgo_tower_free": [vp, i32],
     "sgo_tower_max_positions": [vp, i32],
-    "sgo_selfplay_step": [vp, i32, vp, vp, i32, i32, vp, C.POINTER(i32), vp],
+    "sgo_selfplay_step": [vp, i32, vp, vp, i32, i32, vp, i32, C.POINTER(i32), vp],
     "sgo_record_words": [vp],
     "sgo_records_pack": [vp, vp, vp, vp, vp, vp],
     "sgo_tower_forward": [vp, i32, i32, vp, i32, vp, i32, vp, vp, vp],

@@ -234,7 +234,12 @@ class BatchedGames(object):
         if n == 0:
             return 0
         games = torch.div(idx, e.L, rounding_mode='floor').long()
-        syms = None if syms_game is None else syms_game[games].contiguous()
+        if syms_game is None:
+            syms = None
+        elif syms_game.numel() == e.G * e.L:             # per leaf slot (mode B)
+            syms = syms_game[idx.long()].contiguous()
+        else:
+            syms = syms_game[games].contiguous()
         groups = [(0, idx, syms)]
         if not self.same_model:
             mm = cur_model_dev[games]
@@ -248,13 +253,14 @@ class BatchedGames(object):
         self.eval_count += n
         return n
 
-    def _draw_syms_device(self):
+    def _draw_syms_device(self, per_leaf=False):
         if not self.use_symmetry:
             return None
         r = self.rngs[0]
         seed = int(r.r.randint(1 << 31)) if hasattr(r, "r") else 0
         g = torch.Generator(device=self.eng.device).manual_seed(seed)
-        return torch.randint(0, 7, (self.G,), generator=g, device=self.eng.device, dtype=torch.int32)
+        n = self.G * self.eng.L if per_leaf else self.G
+        return torch.randint(0, 7, (n,), generator=g, device=self.eng.device, dtype=torch.int32)
 
     def _search_native(self, tree_sel_dev, cur_model_dev):
         """The search of one ply through sgo_selfplay_step: the host only loops over steps/waves."""
@@ -263,7 +269,10 @@ class BatchedGames(object):
             self.ev[mi].attach(e, mi)
         mg = None if self.same_model else cur_model_dev.to(torch.int32)
         for _ in range(int(self.sims / self.batch)):
-            n = e.selfplay_step(self.mode, self.batch, self.energy, tree_sel_dev, mg, self._draw_syms_device())
+            if self.mode == 'a':      # one symmetry per game per simulate batch (self_play.py:70)
+                n = e.selfplay_step('a', self.batch, self.energy, tree_sel_dev, mg, sym_game=self._draw_syms_device())
+            else:                     # one symmetry per predict request = per leaf (predicting_queue_worker.py:88-92)
+                n = e.selfplay_step('b', self.batch, self.energy, tree_sel_dev, mg, sym_leaf=self._draw_syms_device(per_leaf=True))
             self.sim_count += n
             self.eval_count += n
 
@@ -280,12 +289,13 @@ class BatchedGames(object):
         e = self.eng
         for _ in range(int(self.sims / self.energy)):
             restart = True
+            syms_wave = self._draw_syms_device(per_leaf=True)               # one draw per leaf slot per wave
             while True:
                 newly, stalled = e.select_b(self.batch, restart, tree_sel_dev)
                 restart = False
                 if newly == 0:
                     break
-                n = self._eval_leaves_device(tree_sel_dev, cur_model_dev, self._draw_syms_device())
+                n = self._eval_leaves_device(tree_sel_dev, cur_model_dev, syms_wave)
                 e.expand(self._pbuf, self._vbuf, tree_sel_dev)
                 self.sim_count += n
                 if stalled == 0:

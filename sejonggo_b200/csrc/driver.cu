@@ -10,9 +10,10 @@
 static inline cudaStream_t S_(void *s) { return (cudaStream_t)s; }
 
 // leaf slots awaiting evaluation whose game uses network slot `want` (model_of_game NULL = all -> slot 0);
-// also expands the per-game symmetry id to per-leaf
+// also gathers the symmetry id of each: per game (mode A: one draw per simulate batch, symmetry.py:128 via
+// self_play.py:70) or per leaf slot (mode B: one draw per put_predict_request, predicting_queue_worker.py:88-92)
 __global__ void k_leaf_gather(const LeafRef *leaf_refs, int total, int L, const int32_t *model_of_game, int want,
-                              const int32_t *sym_game, int32_t *index, int32_t *sym_out, int32_t *count)
+                              const int32_t *sym_in, int sym_per_leaf, int32_t *index, int32_t *sym_out, int32_t *count)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     bool v = i < total && leaf_refs[i].state == 1;
@@ -25,7 +26,7 @@ __global__ void k_leaf_gather(const LeafRef *leaf_refs, int total, int L, const 
     if (v) {
         int o = base + __popc(bal & ((1u << lane) - 1u));
         index[o] = i;
-        if (sym_out) sym_out[o] = sym_game ? sym_game[i / L] : 0;
+        if (sym_out) sym_out[o] = sym_in ? sym_in[sym_per_leaf ? i : i / L] : 0;
     }
 }
 
@@ -46,12 +47,12 @@ extern "C" int sgo_tower_max_positions(sgo_engine *e, int32_t slot);
 
 // evaluate every leaf awaiting evaluation with the network slot(s) and leave policy/value in the
 // per-slot step buffers; returns the number evaluated
-static int eval_pending_leaves(sgo_engine *e, const int32_t *d_model_of_game, const int32_t *d_sym_game, int *n_out, void *stream)
+static int eval_pending_leaves(sgo_engine *e, const int32_t *d_model_of_game, const int32_t *d_sym_game, int sym_per_leaf, int *n_out, void *stream)
 {
     int total = e->G * e->L, done = 0;
     for (int slot = 0; slot < (d_model_of_game ? 2 : 1); slot++) {
         SGO_CUDA_OK(e, cudaMemsetAsync(e->counters + 2, 0, sizeof(int32_t), S_(stream)));
-        k_leaf_gather<<<(total + 255) / 256, 256, 0, S_(stream)>>>(e->leaf_refs, total, e->L, d_model_of_game, slot, d_sym_game,
+        k_leaf_gather<<<(total + 255) / 256, 256, 0, S_(stream)>>>(e->leaf_refs, total, e->L, d_model_of_game, slot, d_sym_game, sym_per_leaf,
                                                                    e->step_index, d_sym_game ? e->step_sym : nullptr, e->counters + 2);
         SGO_LAUNCHED(e);
         SGO_CUDA_OK(e, cudaMemcpyAsync(e->h_pinned + 7, e->counters + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, S_(stream)));
@@ -72,7 +73,8 @@ static int eval_pending_leaves(sgo_engine *e, const int32_t *d_model_of_game, co
 }
 
 extern "C" int sgo_selfplay_step(sgo_engine *e, int32_t mode, const int32_t *d_tree_sel, const int32_t *d_model_of_game,
-                                 int32_t leaves, int32_t total_energy, const int32_t *d_sym_game, int32_t *h_leaves_done, void *stream)
+                                 int32_t leaves, int32_t total_energy, const int32_t *d_sym_game, int32_t sym_per_leaf,
+                                 int32_t *h_leaves_done, void *stream)
 {
     int rc = ensure_step_buffers(e);
     if (rc) return rc;
@@ -80,7 +82,7 @@ extern "C" int sgo_selfplay_step(sgo_engine *e, int32_t mode, const int32_t *d_t
     if (mode == 0) {
         rc = sgo_tree_select_a(e, d_tree_sel, leaves, stream);
         if (rc) return rc;
-        rc = eval_pending_leaves(e, d_model_of_game, d_sym_game, &n, stream);
+        rc = eval_pending_leaves(e, d_model_of_game, d_sym_game, sym_per_leaf, &n, stream);
         if (rc) return rc;
         done = n;
         rc = sgo_tree_expand(e, d_tree_sel, e->step_policy, e->step_value, stream);
@@ -95,7 +97,7 @@ extern "C" int sgo_selfplay_step(sgo_engine *e, int32_t mode, const int32_t *d_t
             if (rc) return rc;
             restart = 0;
             if (counts[0] == 0) break;
-            rc = eval_pending_leaves(e, d_model_of_game, d_sym_game, &n, stream);
+            rc = eval_pending_leaves(e, d_model_of_game, d_sym_game, sym_per_leaf, &n, stream);
             if (rc) return rc;
             done += n;
             rc = sgo_tree_expand(e, d_tree_sel, e->step_policy, e->step_value, stream);

@@ -216,16 +216,17 @@ class Engine(object):
         self._ck(self.lib.sgo_leaf_compact_sync(self.h, self._p(self._compact_buf), C.byref(n), self._stream()))
         return self._compact_buf[:n.value], n.value
 
-    def selfplay_step(self, mode, leaves, total_energy=0, tree_sel=None, model_of_game=None, sym_game=None):
+    def selfplay_step(self, mode, leaves, total_energy=0, tree_sel=None, model_of_game=None, sym_game=None, sym_leaf=None):
         """One search step of every game inside the library (select -> evaluate on the loaded
         network slot(s) -> expand -> backup).  mode 'a' = self_play.simulate, 'b' = one
         async_simulate2 wave.  Returns the number of simulations performed."""
         ts = self.dev(tree_sel, torch.int32)
         mg = self.dev(model_of_game, torch.int32)
-        sg = self.dev(sym_game, torch.int32)
+        sg = self.dev(sym_leaf if sym_leaf is not None else sym_game, torch.int32)     # per leaf slot [G*L] or per game [G]
+        assert sg is None or sg.numel() == (self.G * self.L if sym_leaf is not None else self.G)
         n = C.c_int32(0)
         self._ck(self.lib.sgo_selfplay_step(self.h, 0 if mode in (0, 'a') else 1, self._p(ts), self._p(mg), int(leaves),
-                                            int(total_energy), self._p(sg), C.byref(n), self._stream()))
+                                            int(total_energy), self._p(sg), int(sym_leaf is not None), C.byref(n), self._stream()))
         return n.value
 
     def record_words(self):

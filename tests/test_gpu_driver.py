@@ -25,7 +25,8 @@ def _play(native, mode, self_play, use_symmetry, plies=4, G=12, S=9, sims=32, ba
     return bg, trees
 
 
-@pytest.mark.parametrize("mode,self_play,sym", [('a', True, True), ('a', False, True), ('b', True, False), ('b', False, False)])
+@pytest.mark.parametrize("mode,self_play,sym", [('a', True, True), ('a', False, True), ('b', True, False), ('b', False, False),
+                                                ('b', True, True), ('b', False, True)])
 def test_native_step_equals_composed_calls(mode, self_play, sym):
     a, ta = _play(True, mode, self_play, sym)
     b, tb = _play(False, mode, self_play, sym)
