@@ -205,10 +205,15 @@ __global__ void k_stem_weights(const float *w, __nv_bfloat16 *wb)
 // Dense heads on the fused 1x1-conv features (feat[pos][pix][p0,p1,v0,v1], fp32, post BN+ReLU):
 // policy Dense(2P -> A) + softmax, value Dense(2P -> 256) + ReLU + Dense(256 -> 1) + tanh
 // (model.py:77-92).  A CTA owns FC_PB positions per pass: features sit transposed in shared
-// memory ([feature][position]) so one LDS.128 feeds 4 FMAs, and every weight is read once per
-// FC_PB positions (coalesced over the output index).
+// memory ([feature][position]) so one LDS.128 feeds 4 FMAs.  The weights stream through a
+// double-buffered cp.async stage (FC_KT pixels = 4*FC_KT weight rows at a time), so no global
+// load sits on the FMA chain; a thread owns TWO outputs x FC_PB positions (32 accumulators):
+// warps 0-5 the policy outputs, warps 6-9 the value hidden units, both running over the same
+// pixel loop.  Per output the sum runs bias, then pixels ascending, channel 0 then 1.
 #define FC_PB 16
-#define FC_THREADS 256
+#define FC_THREADS 320
+#define FC_KT 8
+#define FC_VOFF 192                                // first thread of the value half
 
 struct FcArgs {
     int n, S, W, scatter;
@@ -218,73 +223,123 @@ struct FcArgs {
     float *policy, *value;
 };
 
-__global__ void __launch_bounds__(FC_THREADS)
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+static inline int fc_smem_bytes(int P, int A)
+{
+    return (int)sizeof(float) * (4 * P * FC_PB + 2 * FC_KT * (2 * A + 512) + FC_PB * (FC_THREADS / 32));
+}
+
+__global__ void __launch_bounds__(FC_THREADS, 1)
 k_heads_fc(FcArgs h)
 {
     extern __shared__ float fs[];
     const int W = h.W, P = W * W, A = h.S * h.S + 1;
-    float *sfeat = fs;                               // [4P][FC_PB]
-    float *logit = sfeat + (size_t)4 * P * FC_PB;    // [FC_PB][A]
-    float *vpart = logit + FC_PB * A;                // [FC_PB][FC_THREADS/32]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tileF = 2 * A + 512;                   // floats per pixel in a stage: policy rows (ch 0, 1), then value rows (ch 0, 1)
+    float *sfeat = fs;                               // [4P][FC_PB]; re-used as logit [FC_PB][A] once the sums are done (16A <= 64P for S >= 5)
+    float *wt = sfeat + (size_t)4 * P * FC_PB;       // [2][FC_KT][tileF]
+    float *vpart = wt + 2 * FC_KT * tileF;           // [FC_PB][FC_THREADS/32]
+    float *logit = sfeat;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int n_stage = (P + FC_KT - 1) / FC_KT;
+    const bool is_val = t >= FC_VOFF, is_pol = !is_val && 2 * t < A;
+    const int o0 = is_val ? 2 * (t - FC_VOFF) : 2 * t;                 // this thread's outputs o0, o0+1
+    const int rowlen = is_val ? 256 : A;
+    const bool two = o0 + 1 < rowlen;
+
+    auto load_stage = [&](int s, int buf) {
+        for (int pi = 0; pi < FC_KT; pi++) {
+            const int pix = s * FC_KT + pi;
+            if (pix >= P) break;
+            float *dst = wt + (size_t)(buf * FC_KT + pi) * tileF;
+            const float *srcp = h.pfw + (size_t)pix * 2 * A;           // rows (pix*2 + ch), flatten order HWC
+            if (!(A & 1)) { for (int c = t; c < A / 2; c += FC_THREADS) cp_async16(dst + 4 * c, srcp + 4 * c); }   // 8A bytes: 16-B chunks when A is even
+            else { for (int c = t; c < A; c += FC_THREADS) cp_async8(dst + 2 * c, srcp + 2 * c); }
+            const float *srcv = h.v1w + (size_t)pix * 512;
+            if (!(A & 1)) { for (int c = t; c < 128; c += FC_THREADS) cp_async16(dst + 2 * A + 4 * c, srcv + 4 * c); }
+            else { for (int c = t; c < 256; c += FC_THREADS) cp_async8(dst + 2 * A + 2 * c, srcv + 2 * c); }
+        }
+        cp_async_commit();
+    };
+
     for (int base = blockIdx.x * FC_PB; base < h.n; base += gridDim.x * FC_PB) {
         const int np = min(FC_PB, h.n - base);
-        __syncthreads();
-        for (int t = threadIdx.x; t < 4 * P * FC_PB; t += blockDim.x) {
-            int p = t / (4 * P), f = t - p * 4 * P;               // coalesced read of position p's features
-            sfeat[f * FC_PB + p] = p < np ? h.feat[(size_t)(base + p) * 4 * P + f] : 0.f;
+        __syncthreads();                                               // the previous pass is done with logit / vpart
+        load_stage(0, 0);
+        for (int i0 = t; i0 < 4 * P * FC_PB; i0 += 8 * FC_THREADS) {   // 8 independent global loads in flight per thread
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int i = i0 + j * FC_THREADS, p = i / (4 * P);   // coalesced read of position p's features
+                v[j] = (i < 4 * P * FC_PB && p < np) ? h.feat[(size_t)base * 4 * P + i] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int i = i0 + j * FC_THREADS, p = i / (4 * P), f = i - p * 4 * P;
+                if (i < 4 * P * FC_PB) sfeat[f * FC_PB + p] = v[j];
+            }
         }
-        __syncthreads();
-        for (int a0 = threadIdx.x; a0 < A; a0 += blockDim.x) {      // policy logits
-            float acc[FC_PB];
-            const float b = h.pfb[a0];
+        float acc0[FC_PB], acc1[FC_PB];
+        {
+            const float *bias = is_val ? h.v1b : h.pfb;
+            const float b0 = (is_pol || is_val) ? bias[o0] : 0.f, b1 = ((is_pol || is_val) && two) ? bias[o0 + 1] : 0.f;
 #pragma unroll
-            for (int p = 0; p < FC_PB; p++) acc[p] = b;
-            for (int pix = 0; pix < P; pix++) {
+            for (int p = 0; p < FC_PB; p++) { acc0[p] = b0; acc1[p] = b1; }
+        }
+        for (int s = 0; s < n_stage; s++) {
+            if (s + 1 < n_stage) { load_stage(s + 1, (s + 1) & 1); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            __syncthreads();                                           // stage s (and, at s = 0, the features) visible to all
+            if (is_pol || is_val) {
+                for (int pi = 0; pi < FC_KT; pi++) {
+                    const int pix = s * FC_KT + pi;
+                    if (pix >= P) break;
+                    const float *wrow = wt + (size_t)((s & 1) * FC_KT + pi) * tileF + (is_val ? 2 * A : 0);
+                    const float *frow = sfeat + (size_t)(pix * 4 + (is_val ? 2 : 0)) * FC_PB;
 #pragma unroll
-                for (int ch = 0; ch < 2; ch++) {
-                    const float wv = h.pfw[(size_t)(pix * 2 + ch) * A + a0];       // flatten order HWC
-                    const float4 *f4 = reinterpret_cast<const float4 *>(sfeat + (pix * 4 + ch) * FC_PB);
+                    for (int ch = 0; ch < 2; ch++) {
+                        const float w0 = wrow[ch * rowlen + o0], w1 = two ? wrow[ch * rowlen + o0 + 1] : 0.f;
+                        const float4 *f4 = reinterpret_cast<const float4 *>(frow + ch * FC_PB);
 #pragma unroll
-                    for (int q = 0; q < FC_PB / 4; q++) {
-                        float4 f = f4[q];
-                        acc[4 * q] = fmaf(f.x, wv, acc[4 * q]); acc[4 * q + 1] = fmaf(f.y, wv, acc[4 * q + 1]);
-                        acc[4 * q + 2] = fmaf(f.z, wv, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(f.w, wv, acc[4 * q + 3]);
+                        for (int q = 0; q < FC_PB / 4; q++) {
+                            const float4 f = f4[q];
+                            acc0[4 * q] = fmaf(f.x, w0, acc0[4 * q]); acc0[4 * q + 1] = fmaf(f.y, w0, acc0[4 * q + 1]);
+                            acc0[4 * q + 2] = fmaf(f.z, w0, acc0[4 * q + 2]); acc0[4 * q + 3] = fmaf(f.w, w0, acc0[4 * q + 3]);
+                            acc1[4 * q] = fmaf(f.x, w1, acc1[4 * q]); acc1[4 * q + 1] = fmaf(f.y, w1, acc1[4 * q + 1]);
+                            acc1[4 * q + 2] = fmaf(f.z, w1, acc1[4 * q + 2]); acc1[4 * q + 3] = fmaf(f.w, w1, acc1[4 * q + 3]);
+                        }
                     }
                 }
             }
-#pragma unroll
-            for (int p = 0; p < FC_PB; p++) logit[p * A + a0] = acc[p];
+            __syncthreads();                                           // buffer (s & 1) may be refilled; after the last stage: sfeat is free
         }
-        {                                                           // value hidden layer, thread = unit
-            const int j = threadIdx.x;
-            float acc[FC_PB];
-            const float b = h.v1b[j];
-#pragma unroll
-            for (int p = 0; p < FC_PB; p++) acc[p] = b;
-            for (int pix = 0; pix < P; pix++) {
-#pragma unroll
-                for (int ch = 0; ch < 2; ch++) {
-                    const float wv = h.v1w[(size_t)(pix * 2 + ch) * 256 + j];
-                    const float4 *f4 = reinterpret_cast<const float4 *>(sfeat + (pix * 4 + 2 + ch) * FC_PB);
-#pragma unroll
-                    for (int q = 0; q < FC_PB / 4; q++) {
-                        float4 f = f4[q];
-                        acc[4 * q] = fmaf(f.x, wv, acc[4 * q]); acc[4 * q + 1] = fmaf(f.y, wv, acc[4 * q + 1]);
-                        acc[4 * q + 2] = fmaf(f.z, wv, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(f.w, wv, acc[4 * q + 3]);
-                    }
-                }
-            }
-            const float w2 = h.v2w[j];
+        if (is_pol) {
 #pragma unroll
             for (int p = 0; p < FC_PB; p++) {
-                float v = fmaxf(acc[p], 0.f) * w2;
+                logit[p * A + o0] = acc0[p];
+                if (two) logit[p * A + o0 + 1] = acc1[p];
+            }
+        }
+        {                                                               // value: ReLU, Dense(256 -> 1) partial sums per warp
+            const float w2a = is_val ? h.v2w[o0] : 0.f, w2b = is_val ? h.v2w[o0 + 1] : 0.f;
+#pragma unroll
+            for (int p = 0; p < FC_PB; p++) {
+                float v = is_val ? fmaf(fmaxf(acc0[p], 0.f), w2a, fmaxf(acc1[p], 0.f) * w2b) : 0.f;
                 for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(SGO_FULL, v, o);
                 if (lane == 0) vpart[p * (FC_THREADS / 32) + warp] = v;
             }
         }
         __syncthreads();
-        // softmax + outputs: one warp per position (2 positions per warp)
+        // softmax + outputs: one warp per position
         for (int p = warp; p < np; p += FC_THREADS / 32) {
             float mx = -3.4e38f;
             for (int a0 = lane; a0 < A; a0 += 32) mx = fmaxf(mx, logit[p * A + a0]);
@@ -312,7 +367,7 @@ k_heads_fc(FcArgs h)
             }
             if (lane == 0) {
                 float vs = h.v2b[0];
-                for (int w8 = 0; w8 < FC_THREADS / 32; w8++) vs += vpart[p * (FC_THREADS / 32) + w8];
+                for (int w8 = FC_VOFF / 32; w8 < FC_THREADS / 32; w8++) vs += vpart[p * (FC_THREADS / 32) + w8];
                 h.value[orow] = tanhf(vs);
             }
         }
@@ -443,8 +498,7 @@ extern "C" int sgo_tower_load_weights(sgo_engine *e, int32_t slot, const sgo_tow
     SGO_CUDA_OK(e, cudaMalloc(&t->feat, sizeof(float) * 4 * (size_t)P * max_positions));
     k_head_w4<<<1, TW_C, 0, S_(stream)>>>(t->pol_conv_w, t->pol_conv_b, t->val_conv_w, t->val_conv_b, t->head_w4, t->head_b4);
     SGO_CUDA_OK(e, cudaGetLastError());
-    SGO_CUDA_OK(e, cudaFuncSetAttribute(k_heads_fc, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)sizeof(float) * (4 * P * FC_PB + FC_PB * A + FC_PB * (FC_THREADS / 32))));
+    SGO_CUDA_OK(e, cudaFuncSetAttribute(k_heads_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem_bytes(P, A)));
     SGO_CUDA_OK(e, cudaMalloc(&t->err, sizeof(int32_t)));
     SGO_CUDA_OK(e, cudaMemsetAsync(t->err, 0, sizeof(int32_t), S_(stream)));
     int dev = 0;
@@ -527,9 +581,9 @@ extern "C" int sgo_tower_forward(sgo_engine *e, int32_t slot, int32_t which, con
     f.n = n; f.S = t->S; f.W = t->W; f.scatter = scatter; f.index = d_index; f.syms = d_sym; f.feat = t->feat;
     f.pfw = t->pol_fc_w; f.pfb = t->pol_fc_b; f.v1w = t->val_fc1_w; f.v1b = t->val_fc1_b; f.v2w = t->val_fc2_w; f.v2b = t->val_fc2_b;
     f.policy = d_policy; f.value = d_value;
-    int fs = (int)sizeof(float) * (4 * P * FC_PB + FC_PB * e->A + FC_PB * (FC_THREADS / 32));
+    int fs = fc_smem_bytes(P, e->A);
     int fgrid = (n + FC_PB - 1) / FC_PB;
-    if (fgrid > 2 * t->sm_count) fgrid = 2 * t->sm_count;
+    if (fgrid > t->sm_count) fgrid = t->sm_count;
     k_heads_fc<<<fgrid, FC_THREADS, fs, S_(stream)>>>(f);
     SGO_LAUNCHED(e);
     if (prof) { cudaEventRecord(pe[3], S_(stream)); t->prof_pos[t->prof_n++] = n; }
