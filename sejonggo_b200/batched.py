@@ -416,7 +416,12 @@ class BatchedGames(object):
             boards_h = e.export_boards().cpu().numpy()
         elif packed_rec:
             # one packed row per game: board words, move, value, policy_target (sgo_records_pack)
-            rec_h = e.records_pack(tree_sel, index_dev, value).cpu().numpy().view(np.uint32)
+            rec_dev = e.records_pack(tree_sel, index_dev, value)
+            if getattr(self, "_rec_pinned", None) is None:               # device -> pinned host, one copy per ply
+                self._rec_pinned = torch.empty(tuple(rec_dev.shape), dtype=rec_dev.dtype, pin_memory=True)
+            self._rec_pinned.copy_(rec_dev, non_blocking=True)
+            torch.cuda.current_stream(e.device).synchronize()
+            rec_h = self._rec_pinned.numpy().view(np.uint32)
             PW = e.packed_words
             boards_h = rec_h[:, :PW]
             prior_h = rec_h[:, PW + 3:PW + 3 + A].view(np.float32)
