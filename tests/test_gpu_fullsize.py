@@ -54,3 +54,29 @@ def test_config3_one_ply_invariants():
         for b in range(nb):
             assert (np.abs(blocks[b]['w']) <= blocks[b]['n'] + 1e-3).all()
         assert meta['root_count'] == int(count[g].sum()) + 1 or meta['root_count'] == int(count[g].sum())
+
+
+def test_tower_full_batch_is_position_independent():
+    """16,384 positions per forward (the bench's chunk size): every output row depends only on its own position —
+    64 distinct positions tiled over the whole batch give bit-identical rows wherever they sit (tiles straddle
+    positions, 281 tile waves per pair), and equal the rows of a 64-position forward that the small-batch tests pin to
+    the fp32 reference."""
+    from sejonggo_b200 import model
+    from sejonggo_b200.engine import Engine
+    S, N, K = 19, 16384, 64
+    e = Engine(size=S, n_games=N, max_leaves=1, arena_blocks=2)
+    e.reset(0, K)
+    e.random_playouts(seed=11, max_plies=150, first=0, n=K)                   # 64 distinct mid-game positions
+    boards = e.export_boards(0, K).cpu().numpy()
+    e.import_boards(np.tile(boards, (N // K, 1, 1, 1)))
+    m = model.TowerModel("t", size=S, n_blocks=2, seed=3, max_positions=N)
+    idx = torch.arange(N, dtype=torch.int32, device=e.device)
+    pol, val = m.evaluate(e, 0, idx, None, slot=0)
+    m.check(e, 0)
+    pol, val = pol.view(N // K, K, -1), val.view(N // K, K)
+    assert torch.equal(pol, pol[0:1].expand_as(pol)) and torch.equal(val, val[0:1].expand_as(val))
+    m2 = model.TowerModel("t2", params=m.params, max_positions=K)
+    p2, v2 = m2.evaluate(e, 0, idx[:K], None, slot=1)
+    assert torch.equal(p2, pol[0]) and torch.equal(v2, val[0])
+    assert float((pol[0].sum(dim=1) - 1).abs().max()) < 1e-4
+    e.close()
