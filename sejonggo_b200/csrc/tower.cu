@@ -128,55 +128,75 @@ __device__ __forceinline__ void sym_src_t(int S, int sym, int y, int x, int &sy,
 
 // Stem as a tensor-core GEMM: im2col of the (symmetry-transformed) input planes straight from
 // the packed bitboards: col[row(y), x][tap*17 + p] = plane p at (y+ky, x+kx)  (valid conv, Q11).
-// Every value is 0, 1 or +-1, exact in bf16.  One 16-B store per thread-item (8 k's).
-__global__ void __launch_bounds__(256)
+// Every value is 0, 1 or +-1, exact in bf16.  A block takes IM_NP positions at a time: first the
+// 16 stone planes of every cell as one 16-bit mask in shared memory, then one thread per output
+// pixel writes the pixel's whole 384-B row — the 192 k's are unrolled, so tap and plane are
+// compile-time constants (3 ALU ops per element) and every store is a full 32-B sector.
+#define IM_NP 8
+#define IM_THREADS 256
+
+template <int SEC>
+__device__ __forceinline__ void im2col_sector(const uint32_t (&m)[9], uint32_t tmv, __nv_bfloat16 *dst)
+{
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        uint32_t v2[2];
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+            const int k = SEC * 16 + 2 * j + hh, tap = k / 17, p = k - tap * 17;
+            v2[hh] = k >= 153 ? 0u : (p == 16 ? tmv : ((m[tap < 9 ? tap : 0] >> p) & 1u) * 0x3F80u);
+        }
+        w[j] = v2[0] | (v2[1] << 16);
+    }
+    stg256(dst + SEC * 16, w);
+}
+
+__global__ void __launch_bounds__(IM_THREADS)
 k_stem_im2col(const Board *boards, const int32_t *index, const int32_t *syms, int n, int S, __nv_bfloat16 *col /* [rows*(W+1)][TW_STEM_K] */)
 {
-    __shared__ uint16_t cell[SGO_MAXS * SGO_MAXS];
-    __shared__ int s_tm;
-    const int W = S - 2, items_per_px = TW_STEM_K / 8;
-    for (int i = blockIdx.x; i < n; i += gridDim.x) {
-        const int src = index ? index[i] : i;
+    __shared__ uint16_t cell[IM_NP][SGO_MAXS * SGO_MAXS];
+    __shared__ int s_tm[IM_NP];
+    const int W = S - 2, PX = W * W;
+    for (int i0 = blockIdx.x * IM_NP; i0 < n; i0 += gridDim.x * IM_NP) {
+        const int np = min(IM_NP, n - i0);
         __syncthreads();
-        if (src < 0) continue;
-        const Board *bd = boards + src;
-        const int sym = syms ? (syms[i] & 7) : 0;
-        const int tm = bd->to_move, head = bd->head;
-        for (int c = threadIdx.x; c < S * S; c += blockDim.x) {
-            int y = c / S, x = c - y * S, sy, sx;
-            sym_src_t(S, sym, y, x, sy, sx);
+        for (int c = threadIdx.x; c < np * S * S; c += blockDim.x) {
+            const int q = c / (S * S), cc = c - q * S * S;
+            const int src = index ? index[i0 + q] : i0 + q;
             uint32_t m = 0;
+            if (src >= 0) {
+                const Board *bd = boards + src;
+                const int sym = syms ? (syms[i0 + q] & 7) : 0;
+                const int tm = bd->to_move, head = bd->head;
+                int y = cc / S, x = cc - y * S, sy, sx;
+                sym_src_t(S, sym, y, x, sy, sx);
 #pragma unroll
-            for (int k = 0; k < SGO_HIST; k++) {
-                int slot = (head + SGO_HIST - k) & (SGO_HIST - 1);
-                uint32_t bl = (bd->st[slot][0][sy] >> sx) & 1u, wh = (bd->st[slot][1][sy] >> sx) & 1u;
-                uint32_t own = tm == 1 ? bl : wh, opp = tm == 1 ? wh : bl;
-                m |= (own << (2 * k)) | (opp << (2 * k + 1));
-            }
-            cell[c] = (uint16_t)m;
-        }
-        if (threadIdx.x == 0) s_tm = tm;
-        __syncthreads();
-        const uint16_t one = 0x3F80, tmv = s_tm == 1 ? 0x3F80 : 0xBF80;       // bf16 +1 / -1
-        const size_t row0 = (size_t)i * (W + 1) + 1;
-        for (int it = threadIdx.x; it < W * W * items_per_px; it += blockDim.x) {
-            int px = it / items_per_px, k0 = (it - px * items_per_px) * 8;
-            int y = px / W, x = px - y * W;
-            uint16_t v[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                int k = k0 + j, tap = k / 17, p = k - tap * 17;
-                uint16_t val = 0;
-                if (k < 153) {
-                    if (p == 16) val = tmv;
-                    else val = ((cell[(y + tap / 3) * S + x + tap % 3] >> p) & 1u) ? one : (uint16_t)0;
+                for (int k = 0; k < SGO_HIST; k++) {
+                    int slot = (head + SGO_HIST - k) & (SGO_HIST - 1);
+                    uint32_t bl = (bd->st[slot][0][sy] >> sx) & 1u, wh = (bd->st[slot][1][sy] >> sx) & 1u;
+                    uint32_t own = tm == 1 ? bl : wh, opp = tm == 1 ? wh : bl;
+                    m |= (own << (2 * k)) | (opp << (2 * k + 1));
                 }
-                v[j] = val;
-            }
-            uint4 o;
-            o.x = v[0] | ((uint32_t)v[1] << 16); o.y = v[2] | ((uint32_t)v[3] << 16);
-            o.z = v[4] | ((uint32_t)v[5] << 16); o.w = v[6] | ((uint32_t)v[7] << 16);
-            *reinterpret_cast<uint4 *>(col + ((row0 + y) * (W + 1) + x) * TW_STEM_K + k0) = o;
+                if (cc == 0) s_tm[q] = tm;
+            } else if (cc == 0) s_tm[q] = 0;
+            cell[q][cc] = (uint16_t)m;
+        }
+        __syncthreads();
+        for (int it = threadIdx.x; it < np * PX; it += blockDim.x) {
+            const int q = it / PX, px = it - q * PX;
+            const int src = index ? index[i0 + q] : i0 + q;
+            if (src < 0) continue;
+            const int y = px / W, x = px - y * W;
+            uint32_t m[9];
+#pragma unroll
+            for (int tap = 0; tap < 9; tap++) m[tap] = cell[q][(y + tap / 3) * S + x + tap % 3];
+            const uint32_t tmv = s_tm[q] == 1 ? 0x3F80u : 0xBF80u;           // bf16 +1 / -1 (plane 16)
+            __nv_bfloat16 *dst = col + (((size_t)(i0 + q) * (W + 1) + 1 + y) * (W + 1) + x) * TW_STEM_K;
+            im2col_sector<0>(m, tmv, dst); im2col_sector<1>(m, tmv, dst); im2col_sector<2>(m, tmv, dst);
+            im2col_sector<3>(m, tmv, dst); im2col_sector<4>(m, tmv, dst); im2col_sector<5>(m, tmv, dst);
+            im2col_sector<6>(m, tmv, dst); im2col_sector<7>(m, tmv, dst); im2col_sector<8>(m, tmv, dst);
+            im2col_sector<9>(m, tmv, dst); im2col_sector<10>(m, tmv, dst); im2col_sector<11>(m, tmv, dst);
         }
     }
 }
@@ -559,8 +579,9 @@ extern "C" int sgo_tower_forward(sgo_engine *e, int32_t slot, int32_t which, con
     cudaEvent_t *pe = prof ? t->prof_ev + (size_t)t->prof_n * 4 : nullptr;
     if (prof) cudaEventRecord(pe[0], S_(stream));
     // stem = im2col from the bitboards + one pair-kernel GEMM (K = 192) with the bias/ReLU epilogue
-    int g2 = n < 8 * t->sm_count ? n : 8 * t->sm_count;
-    k_stem_im2col<<<g2, 256, 0, S_(stream)>>>(boards, d_index, d_sym, n, t->S, t->stem_col);
+    int g2 = (n + IM_NP - 1) / IM_NP;
+    if (g2 > 8 * t->sm_count) g2 = 8 * t->sm_count;
+    k_stem_im2col<<<g2, IM_THREADS, 0, S_(stream)>>>(boards, d_index, d_sym, n, t->S, t->stem_col);
     SGO_LAUNCHED(e);
     {
         int rc0 = launch_conv(e, t, n, -1, 3, 0, -1, stream, t->n_blocks == 0);
