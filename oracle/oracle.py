@@ -64,6 +64,9 @@ def lib():
         L.orc_simulate_a.argtypes = [C.c_int, vp, vp, C.c_int, C.c_int, EVAL_FN, vp]
         L.orc_find_best_leaf_vl.restype = vp
         L.orc_find_best_leaf_vl.argtypes = [vp, vp, vp]
+        L.orc_node_by_moves.restype = vp
+        L.orc_node_by_moves.argtypes = [vp, vp, C.c_int]
+        L.orc_back_propagation.argtypes = [vp, vp, C.c_int, C.c_int64, C.c_float]
         L.orc_wave_b.argtypes = [C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, EVAL_FN, vp]
         L.orc_make_play.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.c_int]
         L.orc_legal_moves.argtypes = [C.c_int, vp, vp]
@@ -303,6 +306,24 @@ def find_best_leaf_virtual_loss(node):
     if not p:
         return None, None
     return Node(p, owner=False), [int(m) for m in moves[:n.value]]
+
+
+def get_node_by_moves(node, moves):
+    """tree_util.py:27-32; raises like the reference on an invalid path."""
+    mv = np.ascontiguousarray(moves, dtype=np.int32)
+    p = lib().orc_node_by_moves(node.ptr, _p(mv), len(mv))
+    if not p:
+        raise Exception("ERROR: Unable to get node: Invalid moves array")
+    return Node(p, owner=False)
+
+
+def back_propagation(result, node):
+    """nomodel_self_play.py:40-56: result = (leaf dict with 'count'/'value', moves)."""
+    leaf, moves = result
+    mv = np.ascontiguousarray(moves, dtype=np.int32)
+    rc = lib().orc_back_propagation(node.ptr, _p(mv), len(mv), int(leaf.get('count', 0)), float(leaf.get('value', 0)))
+    if rc != 0:
+        raise Exception("ERROR: Unable to get node: Invalid moves array")
 
 
 def async_simulate2(node, board, evaluator, energy, original_player, total_energy=None):

@@ -113,3 +113,89 @@ def test_mcts_nested_selected():                  # tests.py:945-998
     o.simulate(t, board, _dummy_eval, 2, 1)
     assert t.child(0).count == 2 and t.child(0).child(1).count == 1 and t.child(0).child(2).count == 1
     assert t.child(1).count == 0 and t.child(0).value == 2 and t.child(0).mean_value == 1 and t.child(1).value == 0
+
+
+def test_tree_depth():                            # tests.py:723-726, tree_util_tests.py:65-67
+    assert o.Node.from_dict({'subtree': {0: {'p': 1, 'subtree': {}}, 1: {'p': 0, 'subtree': {}}}}).depth == 2
+    assert o.Node.from_dict({'subtree': {0: {'p': 1, 'subtree': {3: {'p': 1, 'subtree': {}}, 4: {'p': 0, 'subtree': {}}}},
+                                         1: {'p': 0, 'subtree': {}}}}).depth == 3
+
+
+def _boards_after(*seqs):
+    out = []
+    for seq in seqs:
+        b, _ = o.game_init(9)
+        for x, y in seq:
+            o.make_play(x, y, b)
+        out.append(b)
+    return out
+
+
+def _checking_eval(expected):
+    """tests.py:756-771 DummyModel: asserts the boards presented, policy[:, 0] = 1, value = 1."""
+    seen = []
+
+    def ev(X):
+        assert X.shape[0] == len(expected)
+        for i, e in enumerate(expected):
+            assert np.array_equal(X[i:i + 1], e), i
+        seen.append(X.shape[0])
+        p = np.zeros((X.shape[0], 82), np.float32)
+        p[:, 0] = 1
+        return p, np.ones(X.shape[0], np.float32)
+
+    return ev, seen
+
+
+def test_model_evaluation_boards():               # tests.py:747-774: leaves (0,0) and (1,0) are evaluated, in that order
+    t = o.Node.from_dict({'subtree': {0: {'p': 1, 'subtree': {}}, 1: {'p': 0, 'subtree': {}}}})
+    board, _ = o.game_init(9)
+    ev, seen = _checking_eval(_boards_after([(0, 0)], [(1, 0)]))
+    o.simulate(t, board, ev, 2, 1)
+    assert seen == [2]
+
+
+def test_model_evaluation_nested_boards():        # tests.py:776-850
+    t = o.Node.from_dict({'subtree': {0: {'p': 1, 'subtree': {1: {'p': 1, 'subtree': {}}, 2: {'p': 0, 'subtree': {}}}},
+                                      1: {'p': 0, 'subtree': {}}}})
+    assert t.depth == 3
+    board, _ = o.game_init(9)
+    ev, seen = _checking_eval(_boards_after([(0, 0), (1, 0)], [(0, 0), (2, 0)]))
+    o.simulate(t, board, ev, 2, 1)
+    assert seen == [2]
+
+
+def test_model_evaluation_other_nested_boards():  # tests.py:852-924
+    t = o.Node.from_dict({'subtree': {0: {'p': 1, 'subtree': {}},
+                                      1: {'p': 0, 'subtree': {0: {'p': 0, 'subtree': {}}, 2: {'p': 1, 'subtree': {}}}}}})
+    assert t.depth == 3
+    board, _ = o.game_init(9)
+    ev, seen = _checking_eval(_boards_after([(0, 0)], [(1, 0), (2, 0)]))
+    o.simulate(t, board, ev, 2, 1)
+    assert seen == [2]
+
+
+def test_small_batch_size():                      # tests.py:926-938
+    t = o.Node.from_dict({'subtree': {0: {'p': 1, 'subtree': {}}, 1: {'p': 0, 'subtree': {}}}})
+    board, _ = o.game_init(9)
+    o.simulate(t, board, _dummy_eval, 1, 1)
+    assert t.child(0).count == 1 and t.child(0).value == -1 and t.child(0).nchild > 0
+    assert t.child(1).count == 0 and t.child(1).value == 0 and t.child(1).nchild == 0
+
+
+def test_get_leaf_by_moves():                     # tree_util_tests.py:126-137
+    t = o.Node.from_dict({'subtree': {0: {'p': 1, 'value': 1, 'subtree': {3: {'p': 1, 'value': 1, 'subtree': {}}, 4: {'p': 0, 'subtree': {}}}},
+                                      1: {'p': 0, 'subtree': {}}}})
+    assert o.get_node_by_moves(t, [0]).move == 0
+    n = o.get_node_by_moves(t, [0, 4])
+    assert n.move == 4 and n.p == 0
+    assert o.get_node_by_moves(t, [1]).move == 1
+    with pytest.raises(Exception):
+        o.get_node_by_moves(t, [0, 8])
+
+
+def test_back_prop():                             # tree_util_tests.py:139-193
+    t = o.Node.from_dict({'subtree': {0: {'p': 1, 'value': 1, 'subtree': {}}, 1: {'p': 0, 'subtree': {}}}})
+    o.back_propagation((dict(count=0, p=0.5, value=1, mean_value=0, virtual_loss=0, subtree={}), [0]), t)
+    assert t.count == 1 and t.value == 1 and t.mean_value == 1
+    assert t.child(0).value == 1 and t.child(0).virtual_loss == 0
