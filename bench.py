@@ -320,7 +320,7 @@ def run_ours(a):
                       share_of_step=prof['conv_ms'] / r['ms'], stem_ms=prof['stem_ms'], heads_ms=prof['heads_ms']),
     )
     if world == 1 and not a.no_cpu:
-        out["cpu_baseline"], _ = _cpu_baseline_dict(a.mode, a.blocks, 1, 2)
+        out["cpu_baseline"], _ = _cpu_baseline_dict(a.mode, a.blocks, 1, 16)    # ~10-15 s of CPU work (bounded sample)
     print(json.dumps(out))
     if world > 1:
         torch.distributed.destroy_process_group()
