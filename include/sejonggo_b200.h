@@ -101,8 +101,9 @@ int sgo_tree_backup_a(sgo_engine *e, const int32_t *d_tree_sel, void *stream);
 /* nomodel_self_play.py:40-56,80-82 back_propagation FIFO (mode B, end of wave) */
 int sgo_tree_backup_b(sgo_engine *e, const int32_t *d_tree_sel, int32_t total_energy, void *stream);
 /* self_play.py:138-152: temperature 0 -> max (count, mean, index); temperature 1 ->
- * sample ~ count using d_u01 f64 [G] (uniforms) ; d_forced int32 [G] >=0 overrides
- * (injected np.random.choice).  d_move_out int32 [G] */
+ * np.random.choice(moves, p=count/total) from ONE uniform d_u01[g] in [0,1) per game, computed as numpy does (fp64 p,
+ * sequential cumulative sum, cdf /= cdf[-1], first cdf > u); d_forced int32 [G] >= 0 overrides (injected choice).
+ * d_move_out int32 [G] */
 int sgo_tree_pick(sgo_engine *e, const int32_t *d_tree_sel, const int32_t *d_temperature, const double *d_u01,
                   const int32_t *d_forced, int32_t *d_move_out, void *stream);
 /* self_play.py:223-238: cut every tree of each game to the child `d_moves[g]` (<0 = skip) */

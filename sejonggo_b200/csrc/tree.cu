@@ -467,32 +467,36 @@ __global__ void k_pick(int S, int G, int T, int NB, const NodeBlock *arena, cons
         }
         if (lane == 0) move_out[g] = bs;
     } else {
-        // sample ~ count over children in ascending index (np.random.choice semantics: first
-        // index whose cumulative count exceeds u * total)
-        int cnt[SGO_AWORDS], local = 0;
-        for (int it = 0; it < SGO_AWORDS; it++) {
-            bool e = (nb->exist[it] >> lane) & 1u;
-            cnt[it] = e ? nb->n[it * 32 + lane] : 0;
-            local += cnt[it];
-        }
-        int total = warp_sum(local);
-        double target = (u01 ? u01[g] : 0.5) * (double)total;
-        int run = 0, pick = -1, last = -1;
-        for (int it = 0; it < SGO_AWORDS; it++) {
-            int incl = cnt[it];
-            for (int o = 1; o < 32; o <<= 1) {
-                int v = __shfl_up_sync(SGO_FULL, incl, o);
-                if (lane >= o) incl += v;
+        // np.random.choice(moves, size=1, p=N/total) over the visited children in ascending index (self_play.py:140-149),
+        // reproduced from ONE uniform draw exactly as numpy computes it: p_i = N_i / float(total) in fp64, cdf = sequential
+        // cumulative sum, cdf /= cdf[-1], first index with cdf > u (searchsorted side='right').  The sums are order
+        // dependent in fp64, so one lane walks the children (once per ply per game; tests/test_cpu_choice.py pins the
+        // algorithm against numpy).
+        int local = 0;
+        for (int it = 0; it < SGO_AWORDS; it++)
+            if ((nb->exist[it] >> lane) & 1u) local += nb->n[it * 32 + lane];
+        const int total = warp_sum(local);
+        if (lane == 0) {
+            const int A = S * S + 1;
+            const double u = u01 ? u01[g] : 0.5, tot = (double)total;
+            double fin = 0.0;
+            for (int slot = 0; slot < A; slot++) {
+                if (!((nb->exist[slot >> 5] >> (slot & 31)) & 1u)) continue;
+                const int n = nb->n[slot];
+                if (n > 0) fin = __dadd_rn(fin, __ddiv_rn((double)n, tot));
             }
-            bool hit = cnt[it] > 0 && (double)(run + incl) > target;
-            unsigned bal = __ballot_sync(SGO_FULL, hit);
-            unsigned nz = __ballot_sync(SGO_FULL, cnt[it] > 0);
-            if (nz) last = it * 32 + (31 - __clz(nz));
-            if (bal && pick < 0) pick = it * 32 + (__ffs(bal) - 1);
-            run += __shfl_sync(SGO_FULL, incl, 31);
+            double run = 0.0;
+            int pick = -1, last = -1;
+            for (int slot = 0; slot < A && pick < 0; slot++) {
+                if (!((nb->exist[slot >> 5] >> (slot & 31)) & 1u)) continue;
+                const int n = nb->n[slot];
+                if (n <= 0) continue;
+                run = __dadd_rn(run, __ddiv_rn((double)n, tot));
+                last = slot;
+                if (__ddiv_rn(run, fin) > u) pick = slot;
+            }
+            move_out[g] = pick >= 0 ? pick : last;
         }
-        if (pick < 0) pick = last;
-        if (lane == 0) move_out[g] = pick;
     }
 }
 

@@ -337,3 +337,37 @@ def test_reference_find_best_leaf_cases_on_engine():
     _upload_dict_tree(e, {'subtree': {0: {'p': 1, 'subtree': {}}, 1: {'p': 0, 'subtree': {}}}}, A)
     newly, stalled = e.select_b(3, True)
     assert (newly, stalled) == (2, 1)                    # third selection finds (None, None)
+
+
+def test_pick_temperature1_is_numpy_choice():
+    """k_pick at temperature 1 = np.random.choice(moves, p=N/total) (self_play.py:140-149) from the same uniform draw:
+    fp64 p, sequential cumulative sum, cdf /= cdf[-1], searchsorted 'right' (tests/test_cpu_choice.py pins that
+    algorithm against numpy).  Also temperature 0 = max (count, mean, index)."""
+    from tests.test_cpu_choice import choice_from_u
+    S, G, B = 9, 24, 8
+    e = _engine(size=S, n_games=G, max_leaves=B, arena_blocks=256)
+    e.reset()
+    ev = lambda planes: evaluate(planes, 3, True)
+    mv, _ = e.random_playouts(seed=5, max_plies=6)                      # 24 different roots
+    pol, _ = eval_slots(e, 0, np.arange(G), ev)
+    e.tree_new(pol, force=True)
+    for _ in range(5):
+        step_a(e, ev, B)
+    _, count, value = e.child_stats(want=("count", "value"))
+    count, value = count.cpu().numpy(), value.cpu().numpy()
+    rs = np.random.RandomState(7)
+    for trial in range(8):
+        u = rs.random_sample(G)
+        if trial == 0:
+            u[:4] = [0.0, 1.0 - 2.0 ** -53, 0.5, 1e-300]               # the ends of [0, 1)
+        got = e.pick(np.ones(G, np.int32), u, None).cpu().numpy()
+        for g in range(G):
+            moves = np.nonzero(count[g])[0]
+            assert got[g] == choice_from_u(moves, count[g][moves], u[g]), (trial, g)
+    got0 = e.pick(np.zeros(G, np.int32), None, None).cpu().numpy()
+    legal = e.legal_masks().cpu().numpy()
+    for g in range(G):
+        best = max((int(count[g][a]), np.float32(value[g][a]) / np.float32(count[g][a]) if count[g][a] else np.float32(0), a)
+                   for a in range(S * S + 1) if legal[g][a] == 0)
+        assert got0[g] == best[2], g
+    e.check_errors()
