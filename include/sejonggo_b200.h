@@ -75,6 +75,10 @@ int sgo_random_playouts(sgo_engine *e, int32_t first, int32_t n, uint64_t seed, 
  * `sym` (0..7; or per-position ids d_sym[n] when non-NULL — the reference draws one
  * symmetry per predict batch = per game per step) fused into the gather (symmetry.py:45-114) */
 int sgo_export_planes(sgo_engine *e, int32_t which, int32_t first, int32_t n, int32_t sym, const int32_t *d_sym, float *d_out, void *stream);
+/* the same for an arbitrary list of positions: d_index int32 [n] (games or leaf slots), d_sym int32 [n] or NULL;
+ * the evaluator-protocol path (model.predict_on_batch on host planes) copies only what it asks for */
+int sgo_export_planes_indexed(sgo_engine *e, int32_t which, const int32_t *d_index, int32_t n, const int32_t *d_sym,
+                              float *d_out, void *stream);
 /* symmetry.py "reverse" policy gather (same map, quirk Q8): float32 [n][S*S+1], out of place */
 int sgo_policy_unsym(sgo_engine *e, int32_t n, int32_t sym, const int32_t *d_sym, const float *d_in, float *d_out, void *stream);
 

@@ -78,9 +78,18 @@ def _pick(tree, temperature, rng):
     return o.pick_t0(tree)
 
 
-def _game(models, size, stop_exploration, self_play, num_moves, resigns, rng, komi, root_eval, search):
+def _hook(rng, name, *args):
+    """Optional context callbacks of a replaying rng (begin_root / begin_wave): parity runs that take
+    their symmetry draws from a recorded engine run need to know which request a draw belongs to."""
+    f = getattr(rng, name, None)
+    if f is not None:
+        f(*args)
+
+
+def _game(models, size, stop_exploration, self_play, num_moves, resigns, rng, komi, root_eval, search, on_search=None):
     """Shared body of play_game (self_play.py:164-290) and play_game_async
-    (nomodel_self_play.py:142-271)."""
+    (nomodel_self_play.py:142-271).  on_search(move_n, tree, model) is called after the search of
+    each ply, before the move pick (tests compare the whole tree there)."""
     S = size
     board, player = o.game_init(S)
     model1, model2 = models
@@ -100,6 +109,7 @@ def _game(models, size, stop_exploration, self_play, num_moves, resigns, rng, ko
     for move_n in range(num_moves):
         if move_n == stop_exploration:
             temperature = 0
+        _hook(rng, 'begin_root', move_n)
         policy, value = root_eval(current, board)
         resign = resigns[0] if current is model1 else resigns[1]
         if resign and value <= resign:
@@ -111,6 +121,8 @@ def _game(models, size, stop_exploration, self_play, num_moves, resigns, rng, ko
             if self_play:
                 other_tree = tree
         search(current, board, tree)
+        if on_search is not None:
+            on_search(move_n, tree, current)
         index = _pick(tree, temperature, rng)
         x, y = (index % S, index // S)
         ch = tree.children()
@@ -151,7 +163,7 @@ def _game(models, size, stop_exploration, self_play, num_moves, resigns, rng, ko
 
 
 def play_game(model1, model2, mcts_simulations, stop_exploration, self_play=False, num_moves=None,
-              resign_model1=None, resign_model2=None, size=19, mcts_batch_size=100, rng=None, komi=5.5):
+              resign_model1=None, resign_model2=None, size=19, mcts_batch_size=100, rng=None, komi=5.5, on_search=None):
     """self_play.py:164 (mode A)."""
     def root_eval(model, board):
         p, v = model.predict_on_batch(board)
@@ -164,7 +176,7 @@ def play_game(model1, model2, mcts_simulations, stop_exploration, self_play=Fals
             o.simulate(tree, np.copy(board), lambda b: sym_predict(model, b, sym), mcts_batch_size, op)
 
     gd = _game((model1, model2), size, stop_exploration, self_play, num_moves, (resign_model1, resign_model2),
-               rng, komi, root_eval, search)
+               rng, komi, root_eval, search, on_search)
     gd['modelB_name'], gd['modelW_name'] = gd['modelB'].name, gd['modelW'].name
     gd['winner_model'] = None if gd['winner_model'] is None else gd['winner_model'].name
     return gd
@@ -172,7 +184,7 @@ def play_game(model1, model2, mcts_simulations, stop_exploration, self_play=Fals
 
 def play_game_async(model1_indicator, model2_indicator, energy, stop_exploration, process_id, self_play=False,
                     num_moves=None, resign_model1=None, resign_model2=None, size=19, conf_sims=1600,
-                    conf_energy=8, rng=None, komi=5.5, predict=None, names=None):
+                    conf_energy=8, rng=None, komi=5.5, predict=None, names=None, on_search=None):
     """nomodel_self_play.py:142 (mode B).  `predict(indicator, boards, sym)` stands
     for put_predict_request; `*_SYM` indicators draw one symmetry per request."""
     class Tag(object):
@@ -189,13 +201,14 @@ def play_game_async(model1_indicator, model2_indicator, energy, stop_exploration
 
     def search(tag, board, tree):
         op = int(board[0, 0, 0, 16])
-        for _ in range(int(conf_sims / conf_energy)):                 # nomodel_self_play.py:116
+        for w in range(int(conf_sims / conf_energy)):                 # nomodel_self_play.py:116
+            _hook(rng, 'begin_wave', w)
             o.async_simulate2(tree, np.copy(board), lambda b: one(tag, b), energy, op, total_energy=conf_energy)
 
     t1 = Tag(model1_indicator)
     t2 = t1 if model2_indicator == model1_indicator else Tag(model2_indicator)
     gd = _game((t1, t2), size, stop_exploration, self_play, num_moves, (resign_model1, resign_model2),
-               rng, komi, one, search)
+               rng, komi, one, search, on_search)
     names = names or {}
     gd['modelB_name'] = names.get(gd['modelB'].t, gd['modelB'].t)
     gd['modelW_name'] = names.get(gd['modelW'].t, gd['modelW'].t)

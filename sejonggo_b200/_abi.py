@@ -38,6 +38,7 @@ _PROTOS = {
     "sgo_export_packed": [vp, i32, i32, i32, vp, vp],
     "sgo_random_playouts": [vp, i32, i32, u64, i32, vp, vp, vp],
     "sgo_export_planes": [vp, i32, i32, i32, i32, vp, vp, vp],
+    "sgo_export_planes_indexed": [vp, i32, vp, i32, vp, vp, vp],
     "sgo_policy_unsym": [vp, i32, i32, vp, vp, vp, vp],
     "sgo_tree_new": [vp, vp, vp, vp, f64, i32, vp],
     "sgo_tree_reset": [vp, vp],

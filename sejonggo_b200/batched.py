@@ -52,13 +52,7 @@ class HostModelAdapter(object):
         """idx: int64 device tensor of position indices (games or leaf slots);
         syms: int32 device tensor [len(idx)] or None.  Returns device (policy [k,A], value [k])."""
         k = int(idx.numel())
-        lim = engine.G * engine.L if which else engine.G
-        if syms is None:
-            planes = engine.export_planes(which, 0, lim)[idx]
-        else:
-            full = torch.zeros(lim, dtype=torch.int32, device=engine.device)
-            full[idx] = syms
-            planes = engine.export_planes(which, 0, lim, syms=full)[idx]
+        planes = engine.export_planes_indexed(which, idx, syms)         # only the requested positions leave the device
         p, v = self.model.predict_on_batch(planes.cpu().numpy())
         p = torch.as_tensor(np.ascontiguousarray(p, dtype=np.float32)).to(engine.device).reshape(k, engine.A)
         v = torch.as_tensor(np.ascontiguousarray(v, dtype=np.float32)).to(engine.device).reshape(k)
@@ -111,8 +105,11 @@ class BatchedGames(object):
         self.eng = engine or Engine(size=size, n_games=n_games, trees_per_game=T, max_leaves=self.batch,
                                     arena_blocks=arena_blocks, komi=komi, device=device)
         self.resign = [self._per_game(resign[0]), self._per_game(resign[1])]
-        # device fast path: every evaluator is a GPU tower and draws are not injected per game
-        self.fast = all(hasattr(ev, "is_sgo_evaluator") for ev in self.ev) and rngs is None
+        # device fast path: every evaluator is a GPU tower and no rng injects recorded picks (per-game rngs that
+        # allow device-side sampling keep it: their coin / noise / root-symmetry draws stay per game)
+        self.fast = all(hasattr(ev, "is_sgo_evaluator") for ev in self.ev) and \
+            (rngs is None or all(getattr(r, "device_pick", False) for r in rngs))
+        self.after_search = None      # parity hook: called as after_search(self, tree_sel) between the search and the move pick
         # with GPU towers the whole search step runs inside the library (sgo_selfplay_step)
         self.native_step = native_step and self.fast and all(hasattr(ev, "attach") for ev in self.ev)
         self.sim_count = 0            # leaves expanded + backed up (the north-star "simulations")
@@ -268,7 +265,8 @@ class BatchedGames(object):
         for mi in ((0,) if self.same_model else (0, 1)):
             self.ev[mi].attach(e, mi)
         mg = None if self.same_model else cur_model_dev.to(torch.int32)
-        for _ in range(int(self.sims / self.batch)):
+        # self_play.py:128 int(sims / MCTS_BATCH_SIZE) simulate calls; nomodel_self_play.py:116 int(SIMS / conf ENERGY) waves (Q17)
+        for _ in range(int(self.sims / (self.batch if self.mode == 'a' else self.energy))):
             if self.mode == 'a':      # one symmetry per game per simulate batch (self_play.py:70)
                 n = e.selfplay_step('a', self.batch, self.energy, tree_sel_dev, mg, sym_game=self._draw_syms_device())
             else:                     # one symmetry per predict request = per leaf (predicting_queue_worker.py:88-92)
@@ -386,6 +384,8 @@ class BatchedGames(object):
             self._search_b(tree_sel, active, cur_model)
         else:
             self._search_b_fast(tree_sel, active, cur_model)
+        if self.after_search is not None:
+            self.after_search(self, tree_sel)
         # move pick (self_play.py:138-152)
         forced = None
         u01 = None

@@ -26,6 +26,11 @@
 #ifndef PR_WIDE_LDST
 #define PR_WIDE_LDST 1                  // 256-bit epilogue loads/stores (one full 32-B sector per lane per instruction): +2% on the convs
 #endif
+#ifdef SGO_CONV_ABLATE
+#define PR_DBG(bit) ((a.dbg & (bit)) != 0)
+#else
+#define PR_DBG(bit) false                // the shipped library has no switch that makes the timed kernel skip work
+#endif
 #define PR_SLABS 3
 #define PR_SLAB_BYTES (21 * 1024)                  // >= (128 + 2 * (P + 1)) * 128 for P <= 18
 #define PR_BSTAGES 8
@@ -40,8 +45,8 @@ struct PairMaps {
 struct PairArgs {
     int W, P, rows_per_pos, YB, n_tiles, w_row0, relu;
     int n_taps, kchunks, halo;                // 9 x 4, halo P+1 for the tower convs; 1 x 3, halo 0 for the stem GEMM over the im2col tensor
-    int dbg;                                  // timing ablations only (SGO_CONV_DEBUG): 1 = no epilogue global traffic, 2 = no A loads, 4 = no B loads,
-                                              // 32 = no activation stores, 64 = no skip loads
+    int dbg;                                  // timing ablations, compiled in only with -DSGO_CONV_ABLATE (tools/conv_variants.py): 1 = no epilogue
+                                              // global traffic, 2 = no A loads, 4 = no B loads, 32 = no activation stores, 64 = no skip loads
     const float *bias;
     const __nv_bfloat16 *skip;
     __nv_bfloat16 *out;                       // nullptr: do not store the activations (last layer feeding only the heads)
@@ -154,7 +159,7 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
             const bool leader = elect_one();
             uint32_t slab = 0, sphase = 0, stage = 0, phase = 0;
             const uint32_t slab_bytes = (uint32_t)(128 + 2 * a.halo) * 128u;
-            const bool no_a = a.dbg & 2, no_b = a.dbg & 4;
+            const bool no_a = PR_DBG(2), no_b = PR_DBG(4);
             bool ok = true;
             for (int tile = pair; tile < a.n_tiles && ok; tile += n_pairs) {
                 const int q_lo = tile * 256 + (int)rank * 128 - a.halo;          // first slab row (may be < 0: zero filled)
@@ -238,7 +243,7 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
             const int q = tile * 256 + r;
             const int yb = q / a.P, x = q - yb * a.P;
             bool valid = x < a.W && yb < a.YB && (yb % a.rows_per_pos) != 0;         // pad pixels / pad rows stay zero
-            if (a.dbg & 1) valid = false;
+            if (PR_DBG(1)) valid = false;
             const size_t gofs = (size_t)q * TW_C;
             if (valid && a.skip) {                                   // idle until the MMAs finish: pull the skip row towards L2
 #pragma unroll
@@ -253,7 +258,7 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
 #pragma unroll 1
             for (int c = 0; c < TW_C / 32; c++) {                    // (software-pipelining the TMEM loads over a fully
                 uint32_t sk[16];                                     //  unrolled loop was measured slower: profiles/r01_conv_epilogue_ab.json)
-                const bool do_skip = valid && a.skip && !(a.dbg & 64);
+                const bool do_skip = valid && a.skip && !PR_DBG(64);
                 if (do_skip) {
 #if PR_WIDE_LDST
                     ldg256(a.skip + gofs + c * 32, sk);
@@ -286,7 +291,7 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
                             h0 = fmaf(f1, wb.x, h0); h1 = fmaf(f1, wb.y, h1); h2 = fmaf(f1, wb.z, h2); h3 = fmaf(f1, wb.w, h3);
                         }
                     }
-                    if (a.out && !(a.dbg & 32)) {
+                    if (a.out && !PR_DBG(32)) {
 #if PR_WIDE_LDST
                         stg256(a.out + gofs + c * 32, ow);
                         stg256(a.out + gofs + c * 32 + 16, ow + 8);

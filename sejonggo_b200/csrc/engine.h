@@ -13,7 +13,6 @@ struct sgo_engine {
     Board *leaf_boards;           // [G*L]
     LeafRef *leaf_refs;           // [G*L]
     int32_t *leaf_count;          // [G] leaves selected by the last select
-    uint32_t *leaf_masks;         // [G*L][12] illegal-action words of each leaf position
     NodeBlock *arena;             // [G*T][2][NB]
     TreeMeta *meta;               // [G*T]
     double *root_p64;             // [G*T][APAD]

@@ -168,13 +168,13 @@ __device__ __forceinline__ void sym_src(int S, int sym, int y, int x, int &sy, i
 
 // float32 planes [n][S][S][17] with the symmetry gather fused: one block per position,
 // the 16 bitboards staged in shared memory, output written fully coalesced.
-__global__ void k_export_planes(const Board *boards, int S, int first, int n, int sym, const int32_t *syms, float *out)
+__global__ void k_export_planes(const Board *boards, int S, int first, const int32_t *index, int n, int sym, const int32_t *syms, float *out)
 {
     __shared__ uint32_t rows[16][SGO_ROWW];
     __shared__ int tm_s;
     int g = blockIdx.x;
     if (g >= n) return;
-    const Board *b = boards + first + g;
+    const Board *b = boards + (index ? index[g] : first + g);
     int tm = b->to_move, head = b->head;
     if (syms) sym = syms[g] & 7;
     for (int i = threadIdx.x; i < 16 * SGO_ROWW; i += blockDim.x) {
@@ -287,7 +287,6 @@ extern "C" int sgo_create(const sgo_config *cfg, sgo_engine **out)
     SGO_CUDA_OK(e, cudaMalloc(&e->leaf_boards, sizeof(Board) * GL));
     SGO_CUDA_OK(e, cudaMalloc(&e->leaf_refs, sizeof(LeafRef) * GL));
     SGO_CUDA_OK(e, cudaMalloc(&e->leaf_count, sizeof(int32_t) * e->G));
-    SGO_CUDA_OK(e, cudaMalloc(&e->leaf_masks, sizeof(uint32_t) * SGO_AWORDS * GL));
     SGO_CUDA_OK(e, cudaMalloc(&e->arena, sizeof(NodeBlock) * GT * 2 * e->NB));
     SGO_CUDA_OK(e, cudaMalloc(&e->meta, sizeof(TreeMeta) * GT));
     SGO_CUDA_OK(e, cudaMalloc(&e->root_p64, sizeof(double) * SGO_APAD * GT));
@@ -318,7 +317,7 @@ extern "C" int sgo_destroy(sgo_engine *e)
     sgo_tower_free(e, 0);
     sgo_tower_free(e, 1);
     cudaFree(e->boards); cudaFree(e->leaf_boards); cudaFree(e->leaf_refs); cudaFree(e->leaf_count);
-    cudaFree(e->leaf_masks); cudaFree(e->arena); cudaFree(e->meta); cudaFree(e->root_p64);
+    cudaFree(e->arena); cudaFree(e->meta); cudaFree(e->root_p64);
     cudaFree(e->step_policy); cudaFree(e->step_value); cudaFree(e->step_index); cudaFree(e->step_sym);
     cudaFree(e->wave); cudaFree(e->err_flags); cudaFree(e->counters); cudaFreeHost(e->h_pinned);
     delete e;
@@ -405,7 +404,17 @@ extern "C" int sgo_export_planes(sgo_engine *e, int32_t which, int32_t first, in
     RANGE_OK(e, first, n, which ? e->G * e->L : e->G);
     if (sym < 0 || sym > 7) return sgo_fail(e, "symmetry id out of range");
     if (n == 0) return 0;
-    k_export_planes<<<n, 256, 0, S_(stream)>>>(which ? e->leaf_boards : e->boards, e->S, first, n, sym, d_sym, d_out);
+    k_export_planes<<<n, 256, 0, S_(stream)>>>(which ? e->leaf_boards : e->boards, e->S, first, nullptr, n, sym, d_sym, d_out);
+    SGO_LAUNCHED(e);
+    return 0;
+}
+
+extern "C" int sgo_export_planes_indexed(sgo_engine *e, int32_t which, const int32_t *d_index, int32_t n, const int32_t *d_sym,
+                                         float *d_out, void *stream)
+{
+    if (n < 0 || n > (which ? e->G * e->L : e->G)) return sgo_fail(e, "export_planes_indexed: n out of range");
+    if (n == 0) return 0;
+    k_export_planes<<<n, 256, 0, S_(stream)>>>(which ? e->leaf_boards : e->boards, e->S, 0, d_index, n, 0, d_sym, d_out);
     SGO_LAUNCHED(e);
     return 0;
 }

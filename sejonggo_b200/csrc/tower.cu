@@ -543,7 +543,11 @@ static int launch_conv(sgo_engine *e, sgo_tower *t, int n, int layer, int in, in
     PairArgs pa;
     pa.W = t->W; pa.P = t->P; pa.rows_per_pos = t->W + 1;
     pa.YB = n * (t->W + 1) + 1;
+#ifdef SGO_CONV_ABLATE
     { const char *d = getenv("SGO_CONV_DEBUG"); pa.dbg = d ? atoi(d) : 0; }
+#else
+    pa.dbg = 0;
+#endif
     pa.n_tiles = (pa.YB * t->P + 255) / 256;
     pa.relu = 1; pa.err = t->err;
     if (layer >= 0) {

@@ -138,6 +138,15 @@ class Engine(object):
         self._ck(self.lib.sgo_export_planes(self.h, which, first, n, int(sym), self._p(sy), self._p(out), self._stream()))
         return out
 
+    def export_planes_indexed(self, which, index, syms=None):
+        """float32 [k][S][S][17] planes of the positions index[k] (games or leaf slots), per-position symmetry ids."""
+        ix = self.dev(index, torch.int32)
+        sy = self.dev(syms, torch.int32)
+        k = int(ix.numel())
+        out = torch.empty((k, self.S, self.S, 17), dtype=torch.float32, device=self.device)
+        self._ck(self.lib.sgo_export_planes_indexed(self.h, which, self._p(ix), k, self._p(sy), self._p(out), self._stream()))
+        return out
+
     def policy_unsym(self, policy, sym=0, syms=None):
         p = self.dev(policy, torch.float32).reshape(-1, self.A)
         out = torch.empty_like(p)

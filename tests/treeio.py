@@ -64,3 +64,29 @@ def engine_rows(blocks, meta, p64, A):
     for i, r in enumerate(rows):
         a[i] = r
     return a
+
+
+def oracle_rows_fast(node):
+    """oracle_rows through the bulk children() export (one ctypes call per expanded node): the same canonical
+    rows, fast enough for 19x19 trees with thousands of expanded nodes."""
+    from oracle import oracle as o
+    L = o.lib()
+    chunks = []
+
+    def rec(ptr, depth):
+        n = o.Node(ptr, owner=False)
+        ch = n.children()
+        k = len(ch['moves'])
+        a = np.zeros(k, dtype=ROW_DTYPE)
+        a['depth'] = depth
+        a['move'], a['count'], a['value'], a['mean'] = ch['moves'], ch['counts'], ch['values'], ch['means']
+        a['p'], a['busy'], a['expanded'] = ch['ps'], ch['busy'], ch['expanded']
+        for i in range(k):
+            chunks.append(a[i:i + 1])
+            if ch['expanded'][i]:
+                rec(L.orc_node_child_at(ptr, i), depth + 1)
+
+    import sys
+    sys.setrecursionlimit(10000)
+    rec(node.ptr, 0)
+    return np.concatenate(chunks) if chunks else np.zeros(0, dtype=ROW_DTYPE)
