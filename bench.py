@@ -223,13 +223,13 @@ def run_ours(a):
         # per game, no noise, temperature 0 from ply 0, 1600 sims/ply, one random symmetry per predict batch
         params2 = model.init_params(SIZE, a.blocks, seed=1)
         m2 = model.TowerModel("model_2", params=params2, max_positions=a.max_positions)
-        arena = a.arena or 2 * (a.sims + batch)
+        arena = a.arena or 4 * (a.sims + batch)
         bg = BatchedGames((m, m2), G, size=SIZE, mode=a.mode, mcts_batch_size=BATCH_A, energy=ENERGY_B, mcts_simulations=a.sims,
                           stop_exploration=0, self_play=False, rng=HostRng(1234 + rank), arena_blocks=arena, device=local,
                           record_boards='packed')
     else:
         m2 = m
-        arena = a.arena or 4 * (SIMS + batch)
+        arena = a.arena or 8 * (SIMS + batch)
         bg = BatchedGames((m, m), G, size=SIZE, mode=a.mode, mcts_batch_size=BATCH_A, energy=ENERGY_B, mcts_simulations=a.sims,
                           stop_exploration=30, self_play=True, rng=HostRng(1234 + rank), arena_blocks=arena, device=local,
                           record_boards='packed')
@@ -306,8 +306,8 @@ def run_ours(a):
                                                            "temperature 0, random symmetry per batch)" if a.match else "self-play",
                                                            a.blocks, a.sims, G, a.mode.upper()),
                     games_per_gpu=G, mode=a.mode, sims_per_ply=a.sims, moves_per_sec=r['plies'] / (r['ms'] * 1e-3),
-                    l2="working set (trees %.1f GB, activations %.1f GB) >> 126 MB L2; no flush needed" %
-                       (G * bg.eng.T * 2 * arena * 6272 / 1e9, 3 * (a.max_positions * 18 + 1) * 18 * 512 / 1e9),
+                    l2="working set (node pool %.1f GB, activations %.1f GB) >> 126 MB L2; no flush needed" %
+                       (G * bg.eng.T * arena * 6272 / 1e9, 3 * (a.max_positions * 18 + 1) * 18 * 512 / 1e9),
                     step="one ply of every game", parallelism="games sharded, %d rank(s)" % world,
                     records_gathered=None if gathered is None else [int(g.numel()) for g in gathered]),
         e2e=dict(value=r2['sims'] / (r2['ms'] * 1e-3), unit="simulations/s", h2d_bytes_per_step=r2['h2d'] / a.steps,

@@ -31,7 +31,7 @@ typedef struct sgo_config {
     int32_t n_games;         /* concurrent games G held in HBM */
     int32_t trees_per_game;  /* 1 self-play (shared tree, Q16), 2 match play */
     int32_t max_leaves;      /* leaves per game per step: MCTS_BATCH_SIZE (mode A) or ENERGY (mode B) */
-    int32_t arena_blocks;    /* node blocks per tree per arena half */
+    int32_t arena_blocks;    /* node blocks per tree ON AVERAGE: all trees share one pool of n_games*trees_per_game*arena_blocks */
     float komi;              /* conf['KOMI'] */
     int32_t reserved[9];
 } sgo_config;
@@ -88,7 +88,16 @@ int sgo_policy_unsym(sgo_engine *e, int32_t n, int32_t sym, const int32_t *d_sym
  * d_policy f32 [G][S*S+1]; d_noise f64 [G][S*S+1] or NULL (add_noise); eps = DIRICHLET_EPSILON */
 int sgo_tree_new(sgo_engine *e, const int32_t *d_tree_sel, const float *d_policy, const double *d_noise,
                  double eps, int32_t force, void *stream);
-int sgo_tree_reset(sgo_engine *e, void *stream);   /* all trees -> None */
+int sgo_tree_reset(sgo_engine *e, void *stream);   /* all trees -> None, every node block back in the pool */
+/* drop every tree of the games with d_game_mask[g] != 0 (int32 [G]) and return their blocks to the pool */
+int sgo_tree_free(sgo_engine *e, const int32_t *d_game_mask, void *stream);
+/* selfplay_worker.py:81-124 — a worker starts its next game as soon as one ends: for the games with
+ * d_game_mask[g] != 0, game_init (play.py:295-299) + drop their trees, leaving every other game untouched */
+int sgo_games_restart(sgo_engine *e, const int32_t *d_game_mask, void *stream);
+/* node blocks each tree owns: d_out int32 [G*trees_per_game] */
+int sgo_tree_sizes(sgo_engine *e, int32_t *d_out, void *stream);
+/* node pool occupancy: h_out[4] = capacity in blocks, free now, fewest free ever seen, failed allocations (synchronises) */
+int sgo_pool_stats_sync(sgo_engine *e, int64_t *h_out, void *stream);
 /* self_play.py:28-66 simulate (mode A) select: descend by top_n[0], take top-`batch`
  * at the frontier, greedy top_one_action below expanded ones; fills the leaf slots */
 int sgo_tree_select_a(sgo_engine *e, const int32_t *d_tree_sel, int32_t batch, void *stream);
@@ -115,7 +124,8 @@ int sgo_tree_reroot(sgo_engine *e, const int32_t *d_moves, void *stream);
 /* root children: d_prior f64 [G][S*S+1] (0 where no child = policy_target, self_play.py:203-205),
  * d_count int32, d_value f32; any may be NULL */
 int sgo_tree_child_stats(sgo_engine *e, const int32_t *d_tree_sel, double *d_prior, int32_t *d_count, float *d_value, void *stream);
-/* raw access for tests / checkpointing: copy a tree's live arena to/from host */
+/* raw access for tests / checkpointing: a tree to/from host memory in canonical form — block 0 is the root, the other
+ * blocks follow in breadth-first slot order, child / parent links are indices into that array; h_meta[0] = 0 */
 int sgo_tree_download_sync(sgo_engine *e, int32_t tree, void *h_blocks, int32_t max_blocks, void *h_meta /*8 x int32*/, double *h_root_p64);
 int sgo_tree_upload_sync(sgo_engine *e, int32_t tree, const void *h_blocks, int32_t n_blocks, const void *h_meta, const double *h_root_p64);
 /* leaf bookkeeping: int32 [G] leaves selected in the last select call */

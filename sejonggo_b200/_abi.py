@@ -42,6 +42,10 @@ _PROTOS = {
     "sgo_policy_unsym": [vp, i32, i32, vp, vp, vp, vp],
     "sgo_tree_new": [vp, vp, vp, vp, f64, i32, vp],
     "sgo_tree_reset": [vp, vp],
+    "sgo_tree_free": [vp, vp, vp],
+    "sgo_games_restart": [vp, vp, vp],
+    "sgo_pool_stats_sync": [vp, vp, vp],
+    "sgo_tree_sizes": [vp, vp, vp],
     "sgo_tree_select_a": [vp, vp, i32, vp],
     "sgo_tree_select_b_sync": [vp, vp, i32, i32, C.POINTER(i32), vp],
     "sgo_tree_expand": [vp, vp, vp, vp, vp],

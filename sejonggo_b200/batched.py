@@ -71,10 +71,16 @@ class BatchedGames(object):
     def __init__(self, models, n_games, size=19, mode='a', mcts_batch_size=100, energy=8, mcts_simulations=1600,
                  stop_exploration=30, self_play=False, num_moves=None, resign=(None, None), komi=5.5,
                  dirichlet_eps=0.25, use_symmetry=True, root_symmetry=None, rng=None, rngs=None, arena_blocks=None,
-                 device=0, record_boards='full', engine=None, native_step=True, names=None):
+                 device=0, record_boards='full', engine=None, native_step=True, names=None, n_total=None,
+                 on_game_start=None, on_game_end=None, rng_for_game=None):
         """models: (model1, model2); pass the same object twice for self-play.
-        resign: (resign_model1, resign_model2), each None, a float, or an array[G].
-        rngs: optional list of per-game rng objects (parity runs); else one shared `rng`."""
+        n_games: concurrent games (slots in HBM); n_total: games to play in all (default n_games) — with more
+        games than slots, a slot starts its next game as soon as one ends.
+        resign: (resign_model1, resign_model2), each None, a float, or an array[G] (per slot; on_game_start(game_id)
+        may return a (r1, r2) pair for the game that is starting, e.g. from a calibration in progress).
+        on_game_end(game_id, game_data) is called as each game finishes.
+        rngs: optional list of per-slot rng objects (parity runs); else one shared `rng`; rng_for_game(game_id)
+        hands each starting game its own rng (parity runs with more games than slots)."""
         self.m1, self.m2 = models
         # names reported in game_data; given explicitly when a tag resolves to another model's network (Q21)
         self.names = names or (getattr(self.m1, "name", "model1"), getattr(self.m2, "name", "model2"))
@@ -83,6 +89,8 @@ class BatchedGames(object):
         if self.same_model:
             self.ev[1] = self.ev[0]
         self.G, self.S, self.A = n_games, size, size * size + 1
+        self.n_total = n_games if n_total is None else int(n_total)
+        self.on_game_start, self.on_game_end, self.rng_for_game = on_game_start, on_game_end, rng_for_game
         self.mode = mode
         self.batch = mcts_batch_size if mode == 'a' else energy
         self.energy = energy
@@ -100,7 +108,10 @@ class BatchedGames(object):
         self.record_boards = record_boards
         steps = int(self.sims / self.batch)
         if arena_blocks is None:
-            arena_blocks = max(256, 4 * (steps * self.batch + self.batch))
+            # node blocks per tree ON AVERAGE (all trees share one pool): a ply adds `sims` blocks and re-rooting
+            # keeps the played child's share r of them, so a tree settles near sims / (1 - r); 8x covers r = 0.875
+            # for every game at once, and a single tree may take far more than its share
+            arena_blocks = max(256, 8 * (steps * self.batch + self.batch))
         T = 1 if self_play else 2
         self.eng = engine or Engine(size=size, n_games=n_games, trees_per_game=T, max_leaves=self.batch,
                                     arena_blocks=arena_blocks, komi=komi, device=device)
@@ -108,10 +119,12 @@ class BatchedGames(object):
         # device fast path: every evaluator is a GPU tower and no rng injects recorded picks (per-game rngs that
         # allow device-side sampling keep it: their coin / noise / root-symmetry draws stay per game)
         self.fast = all(hasattr(ev, "is_sgo_evaluator") for ev in self.ev) and \
-            (rngs is None or all(getattr(r, "device_pick", False) for r in rngs))
+            (rngs is None or all(getattr(r, "device_pick", False) for r in rngs)) and \
+            (rng_for_game is None or getattr(rng_for_game, "device_pick", False))
         self.after_search = None      # parity hook: called as after_search(self, tree_sel) between the search and the move pick
         # with GPU towers the whole search step runs inside the library (sgo_selfplay_step)
         self.native_step = native_step and self.fast and all(hasattr(ev, "attach") for ev in self.ev)
+        self.trees_dropped = 0        # trees given up for lack of pool room (_ensure_pool_room)
         self.sim_count = 0            # leaves expanded + backed up (the north-star "simulations")
         self.eval_count = 0
         self.plies_done = 0
@@ -302,38 +315,103 @@ class BatchedGames(object):
 
     # ------------------------------------------------------------------ run
     def run(self, exact_rng_order=True):
+        """Plays n_total games (default: one per slot) and returns their game_data in game order.  With
+        n_total > n_games a slot starts its next game the ply after one ends (selfplay_worker.py:81-124:
+        the reference's worker loop), so the batch stays full until the games run out."""
         self.start()
-        for _ in range(self.num_moves):
-            if not self.step_ply(exact_rng_order=exact_rng_order):
-                break
+        while self.step_ply(exact_rng_order=exact_rng_order):
+            pass
         return self.finish()
 
     def start(self):
         e, G = self.eng, self.G
         e.reset()
         e.tree_reset()
-        # choose_first_player (play.py:301-306): cur_model[g] in {0,1} indexes (model1, model2)
-        self.cur_model = np.array([0 if self.rngs[g].coin() < .5 else 1 for g in range(G)], np.int32)
-        self.model1_isblack = self.cur_model == 0
-        self.active = np.ones(G, bool)
+        self.active = np.zeros(G, bool)
+        self.cur_model = np.zeros(G, np.int32)
+        self.model1_isblack = np.ones(G, bool)
         self.skipped_last = np.zeros(G, bool)
         self.end_reason = np.array(["PLAYED ALL MOVES"] * G, dtype=object)
         self.player = np.ones(G, np.int32)          # move_data['player'] (lags one ply, self_play.py:236)
         self.moves_rec = [[] for _ in range(G)]
-        self.temperature = 1
-        self.move_n = 0
+        self.move_n = np.zeros(G, np.int32)         # ply counter of the game in each slot
+        self.slot_game = np.full(G, -1, np.int64)   # id of the game a slot is playing
+        self.next_game = 0
+        self.results = {}
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self._begin_games(np.arange(G), fresh=True)
+
+    def _begin_games(self, slots, fresh=False):
+        """Start the next games in `slots` (ascending): coin for the colours (play.py:301-306), thresholds from
+        on_game_start; a re-used slot gets game_init and its trees go back to the pool."""
+        slots = [int(g) for g in slots]
+        started = []
+        for g in slots:
+            gid, r = None, None
+            while self.next_game < self.n_total:               # on_game_start may decline an id (a game another worker claimed)
+                gid = self.next_game
+                self.next_game += 1
+                r = self.on_game_start(gid) if self.on_game_start is not None else None
+                if r is not False:
+                    break
+                gid = None
+            if gid is None:
+                break
+            started.append(g)
+            self.slot_game[g] = gid
+            if self.rng_for_game is not None:
+                self.rngs[g] = self.rng_for_game(gid)
+            # choose_first_player: cur_model[g] in {0,1} indexes (model1, model2)
+            self.cur_model[g] = 0 if self.rngs[g].coin() < .5 else 1
+            self.model1_isblack[g] = self.cur_model[g] == 0
+            self.active[g] = True
+            self.skipped_last[g] = False
+            self.end_reason[g] = "PLAYED ALL MOVES"
+            self.player[g] = 1
+            self.moves_rec[g] = []
+            self.move_n[g] = 0
+            if r is not None:
+                r1, r2 = r
+                self.resign[0][g] = np.nan if r1 is None else r1
+                self.resign[1][g] = np.nan if r2 is None else r2
+        if started and not fresh:
+            mask = np.zeros(self.G, np.int32)
+            mask[started] = 1
+            self.eng.games_restart(mask)
+            self.h2d_bytes += mask.nbytes
+
+    def _end_games(self, slots):
+        """Score and package the games that just ended (before their slots are re-used)."""
+        if len(slots) == 0:
+            return
+        sc = self.eng.score().cpu().numpy()
+        for g in slots:
+            gd = self._game_data(int(g), sc[g])
+            gid = int(self.slot_game[g])
+            self.results[gid] = gd
+            self.slot_game[g] = -1
+            self.moves_rec[g] = []
+            if self.on_game_end is not None:
+                self.on_game_end(gid, gd)
 
     def step_ply(self, exact_rng_order=True, record=True):
         """One ply of every active game.  Returns False when no game is left."""
         e, G, S, A = self.eng, self.G, self.S, self.A
-        active, cur_model, move_n = self.active, self.cur_model, self.move_n
-        if not active.any() or move_n >= self.num_moves:
+        active, cur_model = self.active, self.cur_model
+        # games that have played all their moves end here (the reference's `for move_n in range(num_moves)`)
+        over = active & (self.move_n >= self.num_moves)
+        if over.any():
+            active &= ~over
+            self._end_games(np.nonzero(over)[0])
+        # slots whose game has ended take the next game
+        idle = np.nonzero(~active & (self.slot_game < 0))[0]
+        if len(idle) and self.next_game < self.n_total:
+            self._begin_games(idle)
+        if not active.any():
             return False
-        if move_n == self.stop_exploration:
-            self.temperature = 0
-        temperature = self.temperature
+        move_n = self.move_n
+        temps = np.where(move_n >= self.stop_exploration, 0, 1).astype(np.int32)       # self_play.py:183-184
         tree_sel = np.where(active, 0 if self.self_play else cur_model, -1).astype(np.int32)
         act_idx = np.nonzero(active)[0].astype(np.int64)
         # root evaluation (self_play.py:187 / nomodel_self_play.py:165)
@@ -349,13 +427,16 @@ class BatchedGames(object):
         thr = np.where(cur_model == 0, self.resign[0], self.resign[1])
         with np.errstate(invalid='ignore'):
             resigning = active & ~np.isnan(thr) & (thr != 0) & (value_h <= thr)
-        for g in np.nonzero(resigning)[0]:
-            self.end_reason[g] = "resign"
-        active &= ~resigning
-        if not active.any():
-            return False
+        if resigning.any():
+            for g in np.nonzero(resigning)[0]:
+                self.end_reason[g] = "resign"
+            active &= ~resigning
+            self._end_games(np.nonzero(resigning)[0])
+            if not active.any():
+                return self.next_game < self.n_total
         tree_sel = np.where(active, 0 if self.self_play else cur_model, -1).astype(np.int32)
         act_idx = np.nonzero(active)[0].astype(np.int64)
+        self._ensure_pool_room(int(active.sum()))
         # new trees only where there is no reusable subtree (self_play.py:195-198)
         valid = e.tree_valid(tree_sel).cpu().numpy()
         need = active & (valid == 0)
@@ -384,6 +465,8 @@ class BatchedGames(object):
             self._search_b(tree_sel, active, cur_model)
         else:
             self._search_b_fast(tree_sel, active, cur_model)
+        if not self.native_step:
+            e.check_errors()              # (the native step reports a failed allocation itself)
         if self.after_search is not None:
             self.after_search(self, tree_sel)
         # move pick (self_play.py:138-152)
@@ -395,19 +478,19 @@ class BatchedGames(object):
             prior, count, _ = e.child_stats(tree_sel, want=("prior", "count"))
             prior_h = prior.cpu().numpy()                       # policy_target = root priors (Q14)
             self.d2h_bytes += prior_h.nbytes
-        if temperature == 1 and self.fast:
+        explore = active & (temps == 1)
+        if explore.any() and self.fast:
             u01 = np.array([self.rngs[0].uniform() for _ in range(G)], np.float64)    # device-side sampling
             self.h2d_bytes += u01.nbytes
-        elif temperature == 1:
+        elif explore.any():
             if not record or packed_rec:
                 _, count, _ = e.child_stats(tree_sel, want=("count",))
             count_h = count.cpu().numpy()
             forced = np.full(G, -1, np.int32)
-            for g in act_idx:
+            for g in np.nonzero(explore)[0]:
                 nz = np.nonzero(count_h[g])[0]
                 total = int(count_h[g].sum())
                 forced[g] = self.rngs[g].choice([int(m) for m in nz], [int(count_h[g][m]) / float(total) for m in nz])
-        temps = np.full(G, temperature, np.int32)
         index_dev = e.pick(temps, u01, forced, tree_sel)
         index = index_dev.cpu().numpy()
         self.d2h_bytes += index.nbytes
@@ -429,64 +512,95 @@ class BatchedGames(object):
         if boards_h is not None:
             self.d2h_bytes += boards_h.nbytes
         apply = np.full(G, -1, np.int32)
+        ended = []
         for g in act_idx:
             idx = int(index[g])
             x, y = idx % S, idx // S
             if record:
                 self.moves_rec[g].append(dict(
                     board=None if boards_h is None else (boards_h[g:g + 1].copy() if self.record_boards == 'full' else boards_h[g].copy()),
-                    policy=prior_h[g].copy(), value=value_h[g], move=(x, y), move_n=move_n, player=int(self.player[g])))
+                    policy=prior_h[g].copy(), value=value_h[g], move=(x, y), move_n=int(move_n[g]), player=int(self.player[g])))
             if self.skipped_last[g] and y == S:
                 self.end_reason[g] = "BOTH_PASSED"
                 active[g] = False
+                ended.append(g)
                 continue
             self.skipped_last[g] = y == S
             apply[g] = idx
         # update trees, play the move, swap sides (self_play.py:223-238)
         e.reroot(apply)
-        mover = np.where(apply >= 0, 1 if move_n % 2 == 0 else -1, 0)      # black moves on even plies
+        mover = np.where(apply >= 0, np.where(move_n % 2 == 0, 1, -1), 0)      # black moves on even plies
         e.apply_moves(apply)
         self.h2d_bytes += 2 * apply.nbytes
         moved = apply >= 0
         self.player = np.where(moved, mover, self.player).astype(np.int32)
         self.cur_model = np.where(moved, 1 - cur_model, cur_model).astype(np.int32)
+        self.move_n = np.where(moved, move_n + 1, move_n).astype(np.int32)
         self.plies_done += int(moved.sum())
-        self.move_n += 1
-        return bool(active.any())
+        self._end_games(ended)
+        return bool(active.any()) or self.next_game < self.n_total
+
+    def _ensure_pool_room(self, n_active):
+        """The search of one ply allocates at most `sims` node blocks per game (+ a root).  The reference's trees live
+        in unbounded host memory; here they share a pool, so before each ply the pool must hold that much.  When it
+        does not, the games with the largest trees give theirs up and search this ply from a new tree — what the
+        reference does whenever a tree is empty (self_play.py:195-198) — instead of any game running short mid-search.
+        Counted in `trees_dropped`; never triggered while the pool is sized generously (the default)."""
+        e = self.eng
+        per = int(self.sims / (self.batch if self.mode == 'a' else self.energy)) * (self.batch if self.mode == 'a' else self.energy)
+        need = n_active * (per + 1)
+        free = e.pool_stats()['free']
+        if free >= need:
+            return
+        sizes = e.tree_sizes().cpu().numpy().sum(axis=1)
+        mask = np.zeros(self.G, np.int32)
+        for g in np.argsort(-sizes, kind='stable'):
+            if free >= need or sizes[g] == 0:
+                break
+            mask[g] = 1
+            free += int(sizes[g])
+            self.trees_dropped += 1
+        if mask.any():
+            e.tree_free(mask)
+        if free < need:
+            raise EngineError("MCTS node pool too small for one ply of %d games x %d simulations (capacity %d blocks): raise arena_blocks"
+                              % (n_active, per, e.pool_stats()['capacity']))
 
     def finish(self):
+        """Closes the games still in their slots (cut short by the caller) and returns every game's game_data
+        in game order."""
         self.eng.check_errors()
-        return self._finish(self.model1_isblack, self.end_reason, self.player, self.moves_rec)
+        open_slots = np.nonzero(self.slot_game >= 0)[0]
+        self.active[open_slots] = False
+        self._end_games(open_slots)
+        return [self.results[k] for k in sorted(self.results)]
 
     def _to_move(self):
         # plane 16 of every game (+1 black / -1 white): packed word PW-1
         pk = self.eng.export_packed(0)
         return pk[:, -1].cpu().numpy().astype(np.int32)
 
-    def _finish(self, model1_isblack, end_reason, player, moves_rec):
-        e = self.eng
-        sc = e.score().cpu().numpy()
+    def _game_data(self, g, sc):
+        """game_data of the game in slot g (self_play.py:240-290); sc = its (winner, black, white) score row."""
         ps = {1: "B", 0: "D", -1: "W"}
-        out = []
         n1, n2 = self.names
-        for g in range(self.G):
-            black, white = float(sc[g, 1]), float(sc[g, 2]) + self.komi
-            winner = 1 if black > white else (0 if black == white else -1)
-            if end_reason[g] == "resign":
-                result = "%s+R" % ps[int(player[g])]
-            else:
-                result = "%s+%s" % (ps[winner], abs(black - white))
-            modelB, modelW = (n1, n2) if model1_isblack[g] else (n2, n1)
-            if winner == 0:
-                winner_model = None
-            elif self.mode == 'a':
-                winner_model = n1 if (winner == 1) == bool(model1_isblack[g]) else n2       # self_play.py:261
-            else:
-                # nomodel_self_play.py:246-249 picks between the B/W names with the same test (reference quirk)
-                winner_model = modelB if (winner == 1) == bool(model1_isblack[g]) else modelW
-            out.append(dict(moves=moves_rec[g], modelB_name=modelB, modelW_name=modelW,
-                            winner={1: 1, -1: 0, 0: None}[winner], winner_model=winner_model, result=result,
-                            resign_model1=None if np.isnan(self.resign[0][g]) else float(self.resign[0][g]),
-                            resign_model2=None if np.isnan(self.resign[1][g]) else float(self.resign[1][g]),
-                            end_reason=str(end_reason[g]), model1_isblack=bool(model1_isblack[g])))
-        return out
+        black, white = float(sc[1]), float(sc[2]) + self.komi
+        winner = 1 if black > white else (0 if black == white else -1)
+        if self.end_reason[g] == "resign":
+            result = "%s+R" % ps[int(self.player[g])]
+        else:
+            result = "%s+%s" % (ps[winner], abs(black - white))
+        isblack = bool(self.model1_isblack[g])
+        modelB, modelW = (n1, n2) if isblack else (n2, n1)
+        if winner == 0:
+            winner_model = None
+        elif self.mode == 'a':
+            winner_model = n1 if (winner == 1) == isblack else n2       # self_play.py:261
+        else:
+            # nomodel_self_play.py:246-249 picks between the B/W names with the same test (reference quirk)
+            winner_model = modelB if (winner == 1) == isblack else modelW
+        return dict(moves=self.moves_rec[g], modelB_name=modelB, modelW_name=modelW,
+                    winner={1: 1, -1: 0, 0: None}[winner], winner_model=winner_model, result=result,
+                    resign_model1=None if np.isnan(self.resign[0][g]) else float(self.resign[0][g]),
+                    resign_model2=None if np.isnan(self.resign[1][g]) else float(self.resign[1][g]),
+                    end_reason=str(self.end_reason[g]), model1_isblack=isblack, game_id=int(self.slot_game[g]))

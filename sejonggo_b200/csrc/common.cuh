@@ -42,21 +42,21 @@ struct __align__(16) NodeBlock {
 static_assert(sizeof(NodeBlock) == 6272, "NodeBlock layout");
 
 struct TreeMeta {
-    int32_t side;          // live arena half
-    int32_t n_blocks;      // blocks used in the live half; block 0 is the root
+    int32_t root;          // pool id of the root block (meaningful while valid)
+    int32_t n_blocks;      // blocks this tree owns in the pool
     int32_t valid;         // 0: tree is None / has an empty subtree (self_play.py:195)
     int32_t root_f64;      // root priors are float64 (Dirichlet-noised, play.py:401-403)
     int32_t root_count;    // the root node's own count / value (self_play.py:110-112)
     float root_value;
-    int32_t overflow;      // arena exhausted (sticky)
+    int32_t overflow;      // an allocation for this tree failed: the node pool was exhausted (sticky until the tree is freed)
     int32_t pad;
 };
 
 struct LeafRef {           // one selected leaf = entry `slot` of block `block`
-    int32_t block, slot;
+    int32_t block, slot;   // pool id of the parent block, action slot in it
     int32_t to_move;       // side to move at the leaf position
     int32_t state;         // 0 empty, 1 selected (awaiting evaluation), 2 evaluated/expanded
-    int32_t new_block;     // block allocated for its children
+    int32_t new_block;     // pool id of the block allocated for its children
     float sv;              // signed value to back up
     int32_t pad[2];
 };

@@ -108,6 +108,11 @@ extern "C" int sgo_selfplay_step(sgo_engine *e, int32_t mode, const int32_t *d_t
         if (rc) return rc;
     }
     if (h_leaves_done) *h_leaves_done = done;
+    // a game whose allocation failed ran no (or fewer) simulations in THIS step: say so now, not at the end of the run
+    SGO_CUDA_OK(e, cudaMemcpyAsync(e->h_pinned + 12, e->err_flags, sizeof(int32_t), cudaMemcpyDeviceToHost, S_(stream)));
+    SGO_CUDA_OK(e, cudaStreamSynchronize(S_(stream)));
+    if (e->h_pinned[12] & SGO_ERR_ARENA)
+        return sgo_fail(e, "MCTS node pool exhausted during this search step: raise arena_blocks (sgo_pool_stats_sync shows the low-water mark)", -5);
     return 0;
 }
 
@@ -115,7 +120,7 @@ extern "C" int sgo_selfplay_step(sgo_engine *e, int32_t mode, const int32_t *d_t
 // One record per game per ply, the content of the reference's move_data (self_play.py:207-214)
 // in packed form: [0..PW) packed board (16 planes x W words + to_move), [PW] move index,
 // [PW+1] value bits (f32), [PW+2] tree valid flag, [PW+3 .. PW+3+A) policy target = root priors as f32.
-__global__ void k_records_pack(const Board *boards, int S, int G, int T, int NB, const NodeBlock *arena, const TreeMeta *meta,
+__global__ void k_records_pack(const Board *boards, int S, int G, int T, Pool pool, const TreeMeta *meta,
                                const double *root_p64, const int32_t *tree_sel, const int32_t *moves, const float *values,
                                uint32_t *out, int rec_words)
 {
@@ -149,7 +154,7 @@ __global__ void k_records_pack(const Board *boards, int S, int G, int T, int NB,
         dst[PW + 1] = values ? __float_as_uint(values[g]) : 0u;
         dst[PW + 2] = tv ? 1u : 0u;
     }
-    const NodeBlock *nb = tree_arena(const_cast<NodeBlock *>(arena), NB, tree, m.side);
+    const NodeBlock *nb = pool.blk + (tv ? m.root : 0);
     for (int it = 0; it < SGO_AWORDS; it++) {
         int slot = it * 32 + lane;
         if (slot >= A) continue;
@@ -168,7 +173,7 @@ extern "C" int sgo_record_words(sgo_engine *e)
 extern "C" int sgo_records_pack(sgo_engine *e, const int32_t *d_tree_sel, const int32_t *d_moves, const float *d_values,
                                 uint32_t *d_out, void *stream)
 {
-    k_records_pack<<<(e->G + 3) / 4, 128, 0, S_(stream)>>>(e->boards, e->S, e->G, e->T, e->NB, e->arena, e->meta, e->root_p64,
+    k_records_pack<<<(e->G + 3) / 4, 128, 0, S_(stream)>>>(e->boards, e->S, e->G, e->T, sgo_pool(e), e->meta, e->root_p64,
                                                           d_tree_sel, d_moves, d_values, d_out, sgo_record_words(e));
     SGO_LAUNCHED(e);
     return 0;

@@ -280,6 +280,9 @@ extern "C" int sgo_create(const sgo_config *cfg, sgo_engine **out)
     e->tower[0] = e->tower[1] = nullptr;
     e->step_policy = e->step_value = nullptr; e->step_index = e->step_sym = nullptr;
     e->launches = 0;
+    e->stage = nullptr; e->stage_blocks = 0;
+    e->pool_blocks = (long long)cfg->n_games * cfg->trees_per_game * cfg->arena_blocks;
+    if (e->pool_blocks > 0x7fffffffLL) { delete e; return -1; }
     *out = e;
     SGO_CUDA_OK(e, cudaSetDevice(cfg->device));
     size_t GL = (size_t)e->G * e->L, GT = (size_t)e->G * e->T;
@@ -287,13 +290,17 @@ extern "C" int sgo_create(const sgo_config *cfg, sgo_engine **out)
     SGO_CUDA_OK(e, cudaMalloc(&e->leaf_boards, sizeof(Board) * GL));
     SGO_CUDA_OK(e, cudaMalloc(&e->leaf_refs, sizeof(LeafRef) * GL));
     SGO_CUDA_OK(e, cudaMalloc(&e->leaf_count, sizeof(int32_t) * e->G));
-    SGO_CUDA_OK(e, cudaMalloc(&e->arena, sizeof(NodeBlock) * GT * 2 * e->NB));
+    SGO_CUDA_OK(e, cudaMalloc(&e->arena, sizeof(NodeBlock) * (size_t)e->pool_blocks));
+    SGO_CUDA_OK(e, cudaMalloc(&e->free_list, sizeof(int32_t) * (size_t)e->pool_blocks));
+    SGO_CUDA_OK(e, cudaMalloc(&e->pool_ctl, sizeof(int32_t) * 4));
+    SGO_CUDA_OK(e, cudaMalloc(&e->zero_sel, sizeof(int32_t) * e->G));
+    SGO_CUDA_OK(e, cudaMemset(e->zero_sel, 0, sizeof(int32_t) * e->G));
     SGO_CUDA_OK(e, cudaMalloc(&e->meta, sizeof(TreeMeta) * GT));
     SGO_CUDA_OK(e, cudaMalloc(&e->root_p64, sizeof(double) * SGO_APAD * GT));
     SGO_CUDA_OK(e, cudaMalloc(&e->wave, sizeof(int32_t) * 8 * e->G));
     SGO_CUDA_OK(e, cudaMalloc(&e->err_flags, sizeof(int32_t)));
     SGO_CUDA_OK(e, cudaMalloc(&e->counters, sizeof(int32_t) * 4));
-    SGO_CUDA_OK(e, cudaMallocHost(&e->h_pinned, sizeof(int32_t) * 8));
+    SGO_CUDA_OK(e, cudaMallocHost(&e->h_pinned, sizeof(int32_t) * 16));
     SGO_CUDA_OK(e, cudaMemset(e->err_flags, 0, sizeof(int32_t)));
     SGO_CUDA_OK(e, cudaMemset(e->counters, 0, sizeof(int32_t) * 4));
     SGO_CUDA_OK(e, cudaMemset(e->leaf_refs, 0, sizeof(LeafRef) * GL));
@@ -304,6 +311,8 @@ extern "C" int sgo_create(const sgo_config *cfg, sgo_engine **out)
     SGO_CUDA_OK(e, cudaMemset(e->wave, 0, sizeof(int32_t) * 8 * e->G));
     k_games_reset<<<warp_grid(e->G), WARPS_PER_BLOCK * 32>>>(e->boards, 0, e->G);
     SGO_CUDA_OK(e, cudaGetLastError());
+    int rc = sgo_tree_reset(e, nullptr);                 // metas invalid, every pool block on the free stack
+    if (rc) return rc;
     SGO_CUDA_OK(e, cudaDeviceSynchronize());
     return 0;
 }
@@ -317,7 +326,8 @@ extern "C" int sgo_destroy(sgo_engine *e)
     sgo_tower_free(e, 0);
     sgo_tower_free(e, 1);
     cudaFree(e->boards); cudaFree(e->leaf_boards); cudaFree(e->leaf_refs); cudaFree(e->leaf_count);
-    cudaFree(e->arena); cudaFree(e->meta); cudaFree(e->root_p64);
+    cudaFree(e->arena); cudaFree(e->free_list); cudaFree(e->pool_ctl); cudaFree(e->zero_sel); cudaFree(e->stage);
+    cudaFree(e->meta); cudaFree(e->root_p64);
     cudaFree(e->step_policy); cudaFree(e->step_value); cudaFree(e->step_index); cudaFree(e->step_sym);
     cudaFree(e->wave); cudaFree(e->err_flags); cudaFree(e->counters); cudaFreeHost(e->h_pinned);
     delete e;
@@ -343,6 +353,24 @@ extern "C" int sgo_games_reset(sgo_engine *e, int32_t first, int32_t n, void *st
     k_games_reset<<<warp_grid(n), WARPS_PER_BLOCK * 32, 0, S_(stream)>>>(e->boards, first, n);
     SGO_LAUNCHED(e);
     return 0;
+}
+
+__global__ void k_games_restart(Board *boards, int G, const int32_t *mask)
+{
+    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
+    if (w >= G || !mask[w]) return;
+    uint32_t *p = reinterpret_cast<uint32_t *>(boards + w);
+    for (int i = lane; i < (int)(sizeof(Board) / 4); i += 32) p[i] = 0;
+    __syncwarp();
+    if (lane == 0) { boards[w].head = 0; boards[w].to_move = 1; }
+}
+
+extern "C" int sgo_games_restart(sgo_engine *e, const int32_t *d_game_mask, void *stream)
+{
+    if (!d_game_mask) return sgo_fail(e, "games_restart needs a mask");
+    k_games_restart<<<warp_grid(e->G), WARPS_PER_BLOCK * 32, 0, S_(stream)>>>(e->boards, e->G, d_game_mask);
+    SGO_LAUNCHED(e);
+    return sgo_tree_free(e, d_game_mask, stream);
 }
 
 extern "C" int sgo_apply_moves(sgo_engine *e, int32_t first, int32_t n, const int32_t *d_moves, const int32_t *d_colors, void *stream)

@@ -8,6 +8,11 @@
 // action slots l, l+32, ... so every statistic is read with coalesced 128 B loads
 // and the argmax over <=362 children is a register scan + 5 shuffle steps.
 //
+// Memory: every tree draws its blocks from ONE pool (engine.h Pool): a block is addressed by its pool id, a
+// tree is its root id plus the child / parent links.  Re-rooting (self_play.py:223-238) keeps the chosen
+// child's subtree where it is and returns every other block to the pool, so a game whose search concentrates
+// on one line borrows the room that flatter trees do not need; nothing is copied and nothing is sized per tree.
+//
 // Bit-exactness (SURVEY "hard parts", Q18/Q19): PUCT is evaluated with explicitly
 // rounded float32 ops (__fmul_rn/__fdiv_rn/__fadd_rn, never contracted to FMA),
 // or float64 at a Dirichlet-noised root; ties go to the lowest action index;
@@ -96,13 +101,70 @@ __global__ void k_tree_reset(TreeMeta *meta, int n)
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     TreeMeta m = meta[i];
-    m.n_blocks = 0; m.valid = 0; m.root_f64 = 0; m.root_count = 0; m.root_value = 0.f; m.overflow = 0;
+    m.root = -1; m.n_blocks = 0; m.valid = 0; m.root_f64 = 0; m.root_count = 0; m.root_value = 0.f; m.overflow = 0;
     meta[i] = m;
 }
 
+// every block back on the free stack (ids handed out in ascending order)
+__global__ void k_pool_reset(Pool pool, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pool.free_list[i] = (int32_t)(n - 1 - i);
+    if (i == 0) { pool.ctl[0] = (int32_t)n; pool.ctl[1] = (int32_t)n; pool.ctl[2] = 0; }
+}
+
+// Returns block `start` and all its descendants to the pool, except the subtree hanging off block `keep`
+// (-1: none).  The blocks still to visit form a list threaded through their (now meaningless) parent_block
+// fields, so no stack or queue is needed however large the discarded part is.  Whole warp; returns #freed.
+__device__ int free_subtree(const Pool &pool, int start, int keep, int lane)
+{
+    NodeBlock *pb = pool.blk;
+    if (lane == 0) pb[start].parent_block = -1;                      // list terminator
+    __syncwarp();
+    int head = start, freed = 0;
+    while (head >= 0) {
+        const int b = head;
+        int next = pb[b].parent_block;
+        for (int it = 0; it < SGO_AWORDS; it++) {
+            int ch = pb[b].child[it * 32 + lane];
+            if (ch == keep) ch = -1;
+            const unsigned bal = __ballot_sync(SGO_FULL, ch >= 0);
+            if (!bal) continue;
+            const unsigned higher = lane == 31 ? 0u : (bal & ~((2u << lane) - 1u));
+            const int succ = __shfl_sync(SGO_FULL, ch, higher ? __ffs(higher) - 1 : lane);
+            if (ch >= 0) pb[ch].parent_block = higher ? succ : next;  // chain this block's children in front of the list
+            next = __shfl_sync(SGO_FULL, ch, __ffs(bal) - 1);
+        }
+        if (lane == 0) pool_push(pool, b);
+        freed++;
+        __syncwarp();
+        head = next;
+    }
+    return freed;
+}
+
+// drop the trees of the games flagged in `mask` (NULL = tree_sel-selected trees that are valid): selfplay_worker.py:81-124
+// starts the next game in the same worker; here the slot's blocks go back to the pool first
+__global__ void k_tree_free(int G, int T, Pool pool, TreeMeta *meta, const int32_t *game_mask, const int32_t *tree_sel)
+{
+    int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
+    if (g >= G) return;
+    if (game_mask && !game_mask[g]) return;
+    for (int t = 0; t < T; t++) {
+        if (tree_sel && tree_sel[g] != t) continue;
+        TreeMeta m = meta[g * T + t];
+        if (m.valid && m.root >= 0) free_subtree(pool, m.root, -1, lane);
+        __syncwarp();
+        if (lane == 0) {
+            m.root = -1; m.n_blocks = 0; m.valid = 0; m.root_f64 = 0; m.root_count = 0; m.root_value = 0.f; m.overflow = 0;
+            meta[g * T + t] = m;
+        }
+    }
+}
+
 // play.py:376-421 new_tree / new_subtree at the root
-__global__ void k_tree_new(const Board *boards, int S, int G, int T, int NB, NodeBlock *arena, TreeMeta *meta, double *root_p64,
-                           const int32_t *tree_sel, const float *policy, const double *noise, double keep, double eps, int force)
+__global__ void k_tree_new(const Board *boards, int S, int G, int T, Pool pool, TreeMeta *meta, double *root_p64,
+                           const int32_t *tree_sel, const float *policy, const double *noise, double keep, double eps, int32_t *err)
 {
     __shared__ uint32_t scratch[TREE_WARPS][SGO_AWORDS];
     int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
@@ -111,11 +173,19 @@ __global__ void k_tree_new(const Board *boards, int S, int G, int T, int NB, Nod
     int tree = g * T + (tsel < 0 ? 0 : tsel);
     if (tsel < 0) return;
     TreeMeta m = meta[tree];
-    if (m.valid && !force) return;
+    if (m.valid) return;                                   // (a forced rebuild frees the old tree first: sgo_tree_new)
+    int root = -1;
+    if (lane == 0) {
+        int base = pool_pop(pool, 1);
+        if (base >= 0) root = pool.free_list[base - 1];
+        else { atomicOr(err, SGO_ERR_ARENA); meta[tree].overflow = 1; }
+    }
+    root = __shfl_sync(SGO_FULL, root, 0);
+    if (root < 0) return;
     uint32_t *sc = scratch[threadIdx.x >> 5];
     uint32_t ill = board_illegal(boards + g, S, lane);
     illegal_rows_to_words(ill, S, lane, sc);
-    NodeBlock *nb = tree_arena(arena, NB, tree, m.side);
+    NodeBlock *nb = pool.blk + root;
     int A = S * S + 1;
     double *p64 = root_p64 + (size_t)tree * SGO_APAD;
     for (int it = 0; it < SGO_AWORDS; it++) {
@@ -136,13 +206,13 @@ __global__ void k_tree_new(const Board *boards, int S, int G, int T, int NB, Nod
     }
     if (lane == 0) {
         nb->parent_block = -1; nb->parent_slot = -1;
-        m.n_blocks = 1; m.valid = 1; m.root_f64 = noise ? 1 : 0; m.root_count = 0; m.root_value = 0.f;
+        m.root = root; m.n_blocks = 1; m.valid = 1; m.root_f64 = noise ? 1 : 0; m.root_count = 0; m.root_value = 0.f; m.overflow = 0;
         meta[tree] = m;
     }
 }
 
 // self_play.py:28-66 — mode A selection
-__global__ void k_select_a(const Board *boards, int S, int G, int T, int L, int NB, NodeBlock *arena, TreeMeta *meta,
+__global__ void k_select_a(const Board *boards, int S, int G, int T, int L, Pool pool, TreeMeta *meta,
                            const double *root_p64, const int32_t *tree_sel, int batch, Board *leaf_boards,
                            LeafRef *leaf_refs, int32_t *leaf_count, int32_t *err)
 {
@@ -157,14 +227,14 @@ __global__ void k_select_a(const Board *boards, int S, int G, int T, int L, int 
     if (lane == 0) leaf_count[g] = 0;
     for (int i = lane; i < L; i += 32) leaf_refs[(size_t)g * L + i].state = 0;
     if (!m.valid || tsel < 0) return;
-    NodeBlock *ar = tree_arena(arena, NB, tree, m.side);
+    NodeBlock *ar = pool.blk;
     Board *sb = &sboard[wib];
     board_copy(sb, boards + g, lane);
     double sc[SGO_AWORDS];
     uint32_t ok;
-    int blk = 0;
+    int blk = m.root;
     for (int depth = 0;; depth++) {                       // self_play.py:117-120
-        const double *p64 = (blk == 0 && m.root_f64) ? root_p64 + (size_t)tree * SGO_APAD : nullptr;
+        const double *p64 = (blk == m.root && m.root_f64) ? root_p64 + (size_t)tree * SGO_APAD : nullptr;
         ok = node_scores(ar + blk, p64, false, lane, sc);
         int best = warp_argmax(sc, ok, NEG_INF, lane);
         if (best < 0) { if (lane == 0) atomicOr(err, SGO_ERR_NOACTION); return; }
@@ -183,7 +253,10 @@ __global__ void k_select_a(const Board *boards, int S, int G, int T, int L, int 
         if (lane == 0) ssel[wib][n] = (int16_t)s;
     }
     __syncwarp();
-    if (m.n_blocks + n > NB) {
+    int base = 0;
+    if (lane == 0) base = pool_pop(pool, n);              // one block per leaf, taken before anything is written
+    base = __shfl_sync(SGO_FULL, base, 0);
+    if (base < 0) {                                       // pool exhausted: this game selects nothing this step; the step reports it
         if (lane == 0) { atomicOr(err, SGO_ERR_ARENA); meta[tree].overflow = 1; }
         return;
     }
@@ -204,7 +277,7 @@ __global__ void k_select_a(const Board *boards, int S, int G, int T, int L, int 
         }
         if (lane == 0) {
             LeafRef r;
-            r.block = cb; r.slot = cs; r.to_move = lb->to_move; r.state = 1; r.new_block = m.n_blocks + i; r.sv = 0.f;
+            r.block = cb; r.slot = cs; r.to_move = lb->to_move; r.state = 1; r.new_block = pool.free_list[base - 1 - i]; r.sv = 0.f;
             r.pad[0] = r.pad[1] = 0;
             leaf_refs[li] = r;
         }
@@ -213,7 +286,7 @@ __global__ void k_select_a(const Board *boards, int S, int G, int T, int L, int 
 }
 
 // play.py:391-421 new_subtree for one selected leaf (one warp per leaf slot)
-__global__ void k_expand(const Board *boards, int S, int G, int T, int L, int NB, NodeBlock *arena, const TreeMeta *meta,
+__global__ void k_expand(const Board *boards, int S, int G, int T, int L, Pool pool, const TreeMeta *meta,
                          const int32_t *tree_sel, const Board *leaf_boards, LeafRef *leaf_refs,
                          const float *policy, const float *value)
 {
@@ -226,8 +299,7 @@ __global__ void k_expand(const Board *boards, int S, int G, int T, int L, int NB
     int g = (int)(li / L);
     int tsel = tree_sel ? tree_sel[g] : 0;
     if (tsel < 0) return;
-    int tree = g * T + (tsel < 0 ? 0 : tsel);
-    NodeBlock *ar = tree_arena(arena, NB, tree, meta[tree].side);
+    NodeBlock *ar = pool.blk;
     uint32_t *sc = scratch[threadIdx.x >> 5];
     uint32_t ill = board_illegal(leaf_boards + li, S, lane);
     illegal_rows_to_words(ill, S, lane, sc);
@@ -254,7 +326,7 @@ __global__ void k_expand(const Board *boards, int S, int G, int T, int L, int NB
 }
 
 // self_play.py:108-116 — mode A backup, leaves in rank order, one lane walks
-__global__ void k_backup_a(int G, int T, int L, int NB, NodeBlock *arena, TreeMeta *meta, const int32_t *tree_sel,
+__global__ void k_backup_a(int G, int T, int L, Pool pool, TreeMeta *meta, const int32_t *tree_sel,
                            LeafRef *leaf_refs, const int32_t *leaf_count)
 {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -263,7 +335,7 @@ __global__ void k_backup_a(int G, int T, int L, int NB, NodeBlock *arena, TreeMe
     int tree = g * T + (tsel < 0 ? 0 : tsel);
     TreeMeta m = meta[tree];
     if (!m.valid || tsel < 0) return;
-    NodeBlock *ar = tree_arena(arena, NB, tree, m.side);
+    NodeBlock *ar = pool.blk;
     int n = leaf_count[g];
     for (int i = 0; i < n; i++) {
         LeafRef r = leaf_refs[(size_t)g * L + i];
@@ -314,7 +386,7 @@ __device__ __forceinline__ void backprop_b(NodeBlock *ar, TreeMeta *m, LeafRef *
 #define WV_STALL 4
 
 // tree_util.py:4-24 + nomodel_self_play.py:59-75 — mode B selection (resumable)
-__global__ void k_select_b(const Board *boards, int S, int G, int T, int L, int NB, NodeBlock *arena, TreeMeta *meta,
+__global__ void k_select_b(const Board *boards, int S, int G, int T, int L, Pool pool, TreeMeta *meta,
                            const double *root_p64, const int32_t *tree_sel, int energy, int restart, Board *leaf_boards,
                            LeafRef *leaf_refs, int32_t *leaf_count, int32_t *wave, int32_t *counters, int32_t *err)
 {
@@ -336,17 +408,18 @@ __global__ void k_select_b(const Board *boards, int S, int G, int T, int L, int 
     }
     int stalled = 0, newly = 0;
     if (!m.valid || tsel < 0) energy_left = 0;                  // node['subtree'] == {} -> return (:60-61)
-    NodeBlock *ar = tree_arena(arena, NB, tree, m.side);
+    NodeBlock *ar = pool.blk;
+    const int rootb = m.root;
     while (energy_left > 0) {
         // ---- find_best_leaf_virtual_loss
-        int blk = 0, lslot = -1;
+        int blk = rootb, lslot = -1;
         for (int guard = 0; guard < 8 * SGO_MAXDEPTH; guard++) {
             double sc[SGO_AWORDS];
-            const double *p64 = (blk == 0 && m.root_f64) ? root_p64 + (size_t)tree * SGO_APAD : nullptr;
+            const double *p64 = (blk == rootb && m.root_f64) ? root_p64 + (size_t)tree * SGO_APAD : nullptr;
             uint32_t ok = node_scores(ar + blk, p64, true, lane, sc);
             int s = warp_argmax(sc, ok, -100.0, lane);          // sentinel -100 (play.py:313)
             if (s < 0) {
-                if (blk == 0) break;                            // (None, None)
+                if (blk == rootb) break;                        // (None, None)
                 int pb = ar[blk].parent_block, ps = ar[blk].parent_slot;
                 set_busy(ar + pb, ps, true, lane);              // node['virtual_loss'] = 2; node = parent
                 blk = pb;
@@ -359,8 +432,15 @@ __global__ void k_select_b(const Board *boards, int S, int G, int T, int L, int 
         if (lslot >= 0) {
             set_busy(ar + blk, lslot, true, lane);
             if (ar[blk].n[lslot] > 0) { energy_left--; pre_bp++; continue; }     // :66-69
-            if (tail >= L || m.n_blocks + 1 > NB) {
+            int nblk = -1;
+            if (lane == 0 && tail < L) {
+                int base = pool_pop(pool, 1);
+                if (base >= 0) nblk = pool.free_list[base - 1];
+            }
+            nblk = __shfl_sync(SGO_FULL, nblk, 0);
+            if (nblk < 0) {                                     // no leaf slot / pool exhausted: the wave ends here and the step reports it
                 if (lane == 0) { atomicOr(err, SGO_ERR_ARENA); meta[tree].overflow = 1; }
+                set_busy(ar + blk, lslot, false, lane);
                 energy_left = 0;
                 break;
             }
@@ -384,7 +464,7 @@ __global__ void k_select_b(const Board *boards, int S, int G, int T, int L, int 
             for (int d = depth - 1; d >= 0; d--) board_play(lb, S, spath[wib][d], 0, lane);
             if (lane == 0) {
                 LeafRef r;
-                r.block = blk; r.slot = lslot; r.to_move = lb->to_move; r.state = 1; r.new_block = m.n_blocks; r.sv = 0.f;
+                r.block = blk; r.slot = lslot; r.to_move = lb->to_move; r.state = 1; r.new_block = nblk; r.sv = 0.f;
                 r.pad[0] = r.pad[1] = 0;
                 leaf_refs[li] = r;
             }
@@ -416,7 +496,7 @@ __global__ void k_select_b(const Board *boards, int S, int G, int T, int L, int 
 }
 
 // nomodel_self_play.py:80-82 — the remaining back-props of a wave, FIFO
-__global__ void k_backup_b(int G, int T, int L, int NB, NodeBlock *arena, TreeMeta *meta, const int32_t *tree_sel,
+__global__ void k_backup_b(int G, int T, int L, Pool pool, TreeMeta *meta, const int32_t *tree_sel,
                            LeafRef *leaf_refs, int32_t *wave, int total_energy)
 {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -425,7 +505,7 @@ __global__ void k_backup_b(int G, int T, int L, int NB, NodeBlock *arena, TreeMe
     int tree = g * T + (tsel < 0 ? 0 : tsel);
     TreeMeta m = meta[tree];
     if (!m.valid || tsel < 0) return;
-    NodeBlock *ar = tree_arena(arena, NB, tree, m.side);
+    NodeBlock *ar = pool.blk;
     int32_t *wv = wave + (size_t)g * 8;
     int head = wv[WV_HEAD], tail = wv[WV_TAIL], todo = total_energy - wv[WV_PREBP];
     for (int i = 0; i < todo && head < tail; i++, head++) {
@@ -438,7 +518,7 @@ __global__ void k_backup_b(int G, int T, int L, int NB, NodeBlock *arena, TreeMe
 }
 
 // self_play.py:138-152 — move pick
-__global__ void k_pick(int S, int G, int T, int NB, const NodeBlock *arena, const TreeMeta *meta, const int32_t *tree_sel,
+__global__ void k_pick(int S, int G, int T, Pool pool, const TreeMeta *meta, const int32_t *tree_sel,
                        const int32_t *temperature, const double *u01, const int32_t *forced, int32_t *move_out)
 {
     int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
@@ -448,7 +528,7 @@ __global__ void k_pick(int S, int G, int T, int NB, const NodeBlock *arena, cons
     TreeMeta m = meta[tree];
     if (!m.valid || tsel < 0) { if (lane == 0) move_out[g] = -1; return; }
     if (forced && forced[g] >= 0) { if (lane == 0) move_out[g] = forced[g]; return; }
-    const NodeBlock *nb = tree_arena(const_cast<NodeBlock *>(arena), NB, tree, m.side);
+    const NodeBlock *nb = pool.blk + m.root;
     int temp = temperature ? temperature[g] : 0;
     if (temp == 0) {
         // max over (count, mean_value, action) tuples -> ties to the HIGHER index (Q18)
@@ -500,9 +580,9 @@ __global__ void k_pick(int S, int G, int T, int NB, const NodeBlock *arena, cons
     }
 }
 
-// self_play.py:223-238 — cut each tree of the game to child `move` by a Cheney
-// copy of the kept subtree into the other arena half.
-__global__ void k_reroot(int G, int T, int NB, NodeBlock *arena, TreeMeta *meta, const int32_t *moves)
+// self_play.py:223-238 — cut each tree of the game to the child `move`: the child's block becomes the root
+// where it lies ("mcts_tree['parent'] = None") and every block outside its subtree goes back to the pool.
+__global__ void k_reroot(int G, int T, Pool pool, TreeMeta *meta, const int32_t *moves)
 {
     int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
     if (g >= G) return;
@@ -512,53 +592,99 @@ __global__ void k_reroot(int G, int T, int NB, NodeBlock *arena, TreeMeta *meta,
         int tree = g * T + t;
         TreeMeta m = meta[tree];
         if (!m.valid) continue;
-        NodeBlock *src = tree_arena(arena, NB, tree, m.side);
-        NodeBlock *dst = tree_arena(arena, NB, tree, m.side ^ 1);
-        if (!((src[0].exist[mv >> 5] >> (mv & 31)) & 1u)) continue;       // `index in subtree` false
-        int c = src[0].child[mv];
-        int rc = src[0].n[mv];
-        float rv = src[0].w[mv];
+        NodeBlock *root = pool.blk + m.root;
+        if (!((root->exist[mv >> 5] >> (mv & 31)) & 1u)) continue;        // `index in subtree` false
+        int c = root->child[mv];
+        int rc = root->n[mv];
+        float rv = root->w[mv];
         __syncwarp();
-        if (c < 0) {                                                      // child has subtree {} -> new tree later
-            if (lane == 0) { m.valid = 0; m.n_blocks = 0; m.root_f64 = 0; m.root_count = rc; m.root_value = rv; meta[tree] = m; }
-            continue;
-        }
-        const uint4 *s4 = reinterpret_cast<const uint4 *>(src + c);
-        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-        for (int i = lane; i < (int)(sizeof(NodeBlock) / 16); i += 32) d4[i] = s4[i];
-        __syncwarp();
-        if (lane == 0) { dst[0].parent_block = -1; dst[0].parent_slot = -1; }
-        int f = 1;
-        for (int s = 0; s < f; s++) {
-            for (int it = 0; it < SGO_AWORDS; it++) {
-                int slot = it * 32 + lane;
-                int ch = dst[s].child[slot];
-                unsigned bal = __ballot_sync(SGO_FULL, ch >= 0);
-                if (!bal) continue;
-                int mine = f + __popc(bal & ((1u << lane) - 1u));
-                if (ch >= 0) dst[s].child[slot] = mine;
-                while (bal) {
-                    int l = __ffs(bal) - 1;
-                    bal &= bal - 1;
-                    int old = __shfl_sync(SGO_FULL, ch, l);
-                    const uint4 *a = reinterpret_cast<const uint4 *>(src + old);
-                    uint4 *b = reinterpret_cast<uint4 *>(dst + f);
-                    for (int i = lane; i < (int)(sizeof(NodeBlock) / 16); i += 32) b[i] = a[i];
-                    __syncwarp();
-                    if (lane == 0) { dst[f].parent_block = s; dst[f].parent_slot = it * 32 + l; }
-                    f++;
-                }
-                __syncwarp();
-            }
-        }
+        int freed = free_subtree(pool, m.root, c, lane);                  // c < 0: the whole tree
         if (lane == 0) {
-            m.side ^= 1; m.n_blocks = f; m.root_f64 = 0; m.root_count = rc; m.root_value = rv;
+            if (c < 0) {                                                  // child has subtree {} -> new tree later
+                m.root = -1; m.valid = 0; m.n_blocks = 0;
+            } else {
+                pool.blk[c].parent_block = -1; pool.blk[c].parent_slot = -1;
+                m.root = c; m.n_blocks -= freed;
+            }
+            m.root_f64 = 0; m.root_count = rc; m.root_value = rv;
             meta[tree] = m;
         }
+        __syncwarp();
     }
 }
 
-__global__ void k_child_stats(int S, int G, int T, int NB, const NodeBlock *arena, const TreeMeta *meta, const double *root_p64,
+// Cheney copy of a tree into a compact buffer (block 0 = root, children in breadth-first slot order, links rewritten
+// to buffer indices): the canonical form sgo_tree_download_sync hands to the host.  One warp.
+__global__ void k_tree_export(Pool pool, const TreeMeta *meta, int tree, NodeBlock *dst, int max_blocks, int32_t *n_out)
+{
+    int lane = lane_id();
+    TreeMeta m = meta[tree];
+    if (!m.valid || max_blocks < 1) { if (lane == 0) *n_out = 0; return; }
+    const NodeBlock *src = pool.blk;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src + m.root);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    for (int i = lane; i < (int)(sizeof(NodeBlock) / 16); i += 32) d4[i] = s4[i];
+    __syncwarp();
+    if (lane == 0) { dst[0].parent_block = -1; dst[0].parent_slot = -1; }
+    int f = 1;
+    bool full = false;
+    for (int s = 0; s < f && !full; s++) {
+        for (int it = 0; it < SGO_AWORDS && !full; it++) {
+            int slot = it * 32 + lane;
+            int ch = dst[s].child[slot];
+            unsigned bal = __ballot_sync(SGO_FULL, ch >= 0);
+            if (!bal) continue;
+            if (f + __popc(bal) > max_blocks) { full = true; break; }
+            int mine = f + __popc(bal & ((1u << lane) - 1u));
+            if (ch >= 0) dst[s].child[slot] = mine;
+            while (bal) {
+                int l = __ffs(bal) - 1;
+                bal &= bal - 1;
+                int old = __shfl_sync(SGO_FULL, ch, l);
+                const uint4 *a = reinterpret_cast<const uint4 *>(src + old);
+                uint4 *b = reinterpret_cast<uint4 *>(dst + f);
+                for (int i = lane; i < (int)(sizeof(NodeBlock) / 16); i += 32) b[i] = a[i];
+                __syncwarp();
+                if (lane == 0) { dst[f].parent_block = s; dst[f].parent_slot = it * 32 + l; }
+                f++;
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) *n_out = full ? -f : f;
+}
+
+// the inverse: n blocks in the compact form (block 0 = root, links = buffer indices) into freshly popped pool blocks
+__global__ void k_tree_import(Pool pool, TreeMeta *meta, int tree, const NodeBlock *src, int n, TreeMeta hm, int32_t *err)
+{
+    __shared__ int s_base;
+    int lane = lane_id();
+    if (lane == 0) s_base = n > 0 ? pool_pop(pool, n) : 0;
+    __syncwarp();
+    int base = s_base;
+    if (base < 0) { if (lane == 0) { atomicOr(err, SGO_ERR_ARENA); meta[tree].overflow = 1; } return; }
+    for (int b = 0; b < n; b++) {
+        NodeBlock *d = pool.blk + pool.free_list[base - 1 - b];
+        const uint4 *a = reinterpret_cast<const uint4 *>(src + b);
+        uint4 *o = reinterpret_cast<uint4 *>(d);
+        for (int i = lane; i < (int)(sizeof(NodeBlock) / 16); i += 32) o[i] = a[i];
+        __syncwarp();
+        for (int it = 0; it < SGO_AWORDS; it++) {
+            int c = d->child[it * 32 + lane];
+            if (c >= 0) d->child[it * 32 + lane] = pool.free_list[base - 1 - c];
+        }
+        if (lane == 0 && d->parent_block >= 0) d->parent_block = pool.free_list[base - 1 - d->parent_block];
+        __syncwarp();
+    }
+    if (lane == 0) {
+        hm.root = n > 0 ? pool.free_list[base - 1] : -1;
+        hm.n_blocks = n;
+        if (n == 0) hm.valid = 0;
+        meta[tree] = hm;
+    }
+}
+
+__global__ void k_child_stats(int S, int G, int T, Pool pool, const TreeMeta *meta, const double *root_p64,
                               const int32_t *tree_sel, double *prior, int32_t *count, float *value)
 {
     int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
@@ -566,12 +692,13 @@ __global__ void k_child_stats(int S, int G, int T, int NB, const NodeBlock *aren
     int tsel = tree_sel ? tree_sel[g] : 0;
     int tree = g * T + (tsel < 0 ? 0 : tsel);
     TreeMeta m = meta[tree];
-    const NodeBlock *nb = tree_arena(const_cast<NodeBlock *>(arena), NB, tree, m.side);
+    const bool tv = m.valid && tsel >= 0;
+    const NodeBlock *nb = pool.blk + (tv ? m.root : 0);
     int A = S * S + 1;
     for (int it = 0; it < SGO_AWORDS; it++) {
         int slot = it * 32 + lane;
         if (slot >= A) continue;
-        bool e = m.valid && tsel >= 0 && ((nb->exist[it] >> lane) & 1u);
+        bool e = tv && ((nb->exist[it] >> lane) & 1u);
         size_t o = (size_t)g * A + slot;
         if (prior) prior[o] = e ? (m.root_f64 ? root_p64[(size_t)tree * SGO_APAD + slot] : (double)nb->prior[slot]) : 0.0;
         if (count) count[o] = e ? nb->n[slot] : 0;
@@ -609,14 +736,50 @@ extern "C" int sgo_tree_reset(sgo_engine *e, void *stream)
     int n = e->G * e->T;
     k_tree_reset<<<(n + 127) / 128, 128, 0, S_(stream)>>>(e->meta, n);
     LAUNCH_OK(e);
+    k_pool_reset<<<(unsigned)((e->pool_blocks + 255) / 256), 256, 0, S_(stream)>>>(sgo_pool(e), e->pool_blocks);
+    LAUNCH_OK(e);
+    return 0;
+}
+
+extern "C" int sgo_tree_free(sgo_engine *e, const int32_t *d_game_mask, void *stream)
+{
+    k_tree_free<<<warp_grid(e->G), TREE_WARPS * 32, 0, S_(stream)>>>(e->G, e->T, sgo_pool(e), e->meta, d_game_mask, nullptr);
+    LAUNCH_OK(e);
+    return 0;
+}
+
+__global__ void k_tree_sizes(int n, const TreeMeta *meta, int32_t *out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = meta[i].valid ? meta[i].n_blocks : 0;
+}
+
+extern "C" int sgo_tree_sizes(sgo_engine *e, int32_t *d_out, void *stream)
+{
+    int n = e->G * e->T;
+    k_tree_sizes<<<(n + 127) / 128, 128, 0, S_(stream)>>>(n, e->meta, d_out);
+    LAUNCH_OK(e);
+    return 0;
+}
+
+extern "C" int sgo_pool_stats_sync(sgo_engine *e, int64_t *h_out, void *stream)
+{
+    SGO_CUDA_OK(e, cudaMemcpyAsync(e->h_pinned + 8, e->pool_ctl, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, S_(stream)));
+    SGO_CUDA_OK(e, cudaStreamSynchronize(S_(stream)));
+    h_out[0] = e->pool_blocks; h_out[1] = e->h_pinned[8]; h_out[2] = e->h_pinned[9]; h_out[3] = e->h_pinned[10];
     return 0;
 }
 
 extern "C" int sgo_tree_new(sgo_engine *e, const int32_t *d_tree_sel, const float *d_policy, const double *d_noise,
                             double eps, int32_t force, void *stream)
 {
-    k_tree_new<<<warp_grid(e->G), TREE_WARPS * 32, 0, S_(stream)>>>(e->boards, e->S, e->G, e->T, e->NB, e->arena, e->meta, e->root_p64,
-                                                                   d_tree_sel, d_policy, d_noise, 1.0 - eps, eps, force);
+    if (force) {              // the old trees' blocks go back to the pool in a launch of their own (no pop may race a push)
+        k_tree_free<<<warp_grid(e->G), TREE_WARPS * 32, 0, S_(stream)>>>(e->G, e->T, sgo_pool(e), e->meta, nullptr,
+                                                                        d_tree_sel ? d_tree_sel : e->zero_sel);
+        LAUNCH_OK(e);
+    }
+    k_tree_new<<<warp_grid(e->G), TREE_WARPS * 32, 0, S_(stream)>>>(e->boards, e->S, e->G, e->T, sgo_pool(e), e->meta, e->root_p64,
+                                                                   d_tree_sel, d_policy, d_noise, 1.0 - eps, eps, e->err_flags);
     LAUNCH_OK(e);
     return 0;
 }
@@ -624,7 +787,7 @@ extern "C" int sgo_tree_new(sgo_engine *e, const int32_t *d_tree_sel, const floa
 extern "C" int sgo_tree_select_a(sgo_engine *e, const int32_t *d_tree_sel, int32_t batch, void *stream)
 {
     if (batch < 1 || batch > e->L || batch > 128) return sgo_fail(e, "batch must be 1..min(max_leaves,128)");
-    k_select_a<<<warp_grid(e->G), TREE_WARPS * 32, 0, S_(stream)>>>(e->boards, e->S, e->G, e->T, e->L, e->NB, e->arena, e->meta,
+    k_select_a<<<warp_grid(e->G), TREE_WARPS * 32, 0, S_(stream)>>>(e->boards, e->S, e->G, e->T, e->L, sgo_pool(e), e->meta,
                                                                    e->root_p64, d_tree_sel, batch, e->leaf_boards, e->leaf_refs,
                                                                    e->leaf_count, e->err_flags);
     LAUNCH_OK(e);
@@ -636,7 +799,7 @@ extern "C" int sgo_tree_select_b_sync(sgo_engine *e, const int32_t *d_tree_sel, 
 {
     if (energy < 1 || energy > e->L) return sgo_fail(e, "energy must be 1..max_leaves");
     SGO_CUDA_OK(e, cudaMemsetAsync(e->counters, 0, sizeof(int32_t) * 2, S_(stream)));
-    k_select_b<<<warp_grid(e->G), TREE_WARPS * 32, 0, S_(stream)>>>(e->boards, e->S, e->G, e->T, e->L, e->NB, e->arena, e->meta,
+    k_select_b<<<warp_grid(e->G), TREE_WARPS * 32, 0, S_(stream)>>>(e->boards, e->S, e->G, e->T, e->L, sgo_pool(e), e->meta,
                                                                    e->root_p64, d_tree_sel, energy, restart, e->leaf_boards,
                                                                    e->leaf_refs, e->leaf_count, e->wave, e->counters, e->err_flags);
     LAUNCH_OK(e);
@@ -650,21 +813,21 @@ extern "C" int sgo_tree_expand(sgo_engine *e, const int32_t *d_tree_sel, const f
 {
     size_t n = (size_t)e->G * e->L;
     k_expand<<<(unsigned)((n + TREE_WARPS - 1) / TREE_WARPS), TREE_WARPS * 32, 0, S_(stream)>>>(
-        e->boards, e->S, e->G, e->T, e->L, e->NB, e->arena, e->meta, d_tree_sel, e->leaf_boards, e->leaf_refs, d_policy, d_value);
+        e->boards, e->S, e->G, e->T, e->L, sgo_pool(e), e->meta, d_tree_sel, e->leaf_boards, e->leaf_refs, d_policy, d_value);
     LAUNCH_OK(e);
     return 0;
 }
 
 extern "C" int sgo_tree_backup_a(sgo_engine *e, const int32_t *d_tree_sel, void *stream)
 {
-    k_backup_a<<<(e->G + 63) / 64, 64, 0, S_(stream)>>>(e->G, e->T, e->L, e->NB, e->arena, e->meta, d_tree_sel, e->leaf_refs, e->leaf_count);
+    k_backup_a<<<(e->G + 63) / 64, 64, 0, S_(stream)>>>(e->G, e->T, e->L, sgo_pool(e), e->meta, d_tree_sel, e->leaf_refs, e->leaf_count);
     LAUNCH_OK(e);
     return 0;
 }
 
 extern "C" int sgo_tree_backup_b(sgo_engine *e, const int32_t *d_tree_sel, int32_t total_energy, void *stream)
 {
-    k_backup_b<<<(e->G + 63) / 64, 64, 0, S_(stream)>>>(e->G, e->T, e->L, e->NB, e->arena, e->meta, d_tree_sel, e->leaf_refs, e->wave, total_energy);
+    k_backup_b<<<(e->G + 63) / 64, 64, 0, S_(stream)>>>(e->G, e->T, e->L, sgo_pool(e), e->meta, d_tree_sel, e->leaf_refs, e->wave, total_energy);
     LAUNCH_OK(e);
     return 0;
 }
@@ -672,7 +835,7 @@ extern "C" int sgo_tree_backup_b(sgo_engine *e, const int32_t *d_tree_sel, int32
 extern "C" int sgo_tree_pick(sgo_engine *e, const int32_t *d_tree_sel, const int32_t *d_temperature, const double *d_u01,
                              const int32_t *d_forced, int32_t *d_move_out, void *stream)
 {
-    k_pick<<<warp_grid(e->G), TREE_WARPS * 32, 0, S_(stream)>>>(e->S, e->G, e->T, e->NB, e->arena, e->meta, d_tree_sel, d_temperature,
+    k_pick<<<warp_grid(e->G), TREE_WARPS * 32, 0, S_(stream)>>>(e->S, e->G, e->T, sgo_pool(e), e->meta, d_tree_sel, d_temperature,
                                                                d_u01, d_forced, d_move_out);
     LAUNCH_OK(e);
     return 0;
@@ -680,14 +843,14 @@ extern "C" int sgo_tree_pick(sgo_engine *e, const int32_t *d_tree_sel, const int
 
 extern "C" int sgo_tree_reroot(sgo_engine *e, const int32_t *d_moves, void *stream)
 {
-    k_reroot<<<warp_grid(e->G), TREE_WARPS * 32, 0, S_(stream)>>>(e->G, e->T, e->NB, e->arena, e->meta, d_moves);
+    k_reroot<<<warp_grid(e->G), TREE_WARPS * 32, 0, S_(stream)>>>(e->G, e->T, sgo_pool(e), e->meta, d_moves);
     LAUNCH_OK(e);
     return 0;
 }
 
 extern "C" int sgo_tree_child_stats(sgo_engine *e, const int32_t *d_tree_sel, double *d_prior, int32_t *d_count, float *d_value, void *stream)
 {
-    k_child_stats<<<warp_grid(e->G), TREE_WARPS * 32, 0, S_(stream)>>>(e->S, e->G, e->T, e->NB, e->arena, e->meta, e->root_p64, d_tree_sel,
+    k_child_stats<<<warp_grid(e->G), TREE_WARPS * 32, 0, S_(stream)>>>(e->S, e->G, e->T, sgo_pool(e), e->meta, e->root_p64, d_tree_sel,
                                                                       d_prior, d_count, d_value);
     LAUNCH_OK(e);
     return 0;
@@ -719,16 +882,35 @@ extern "C" int sgo_leaf_compact_sync(sgo_engine *e, int32_t *d_index, int32_t *h
     return 0;
 }
 
+// staging buffer for tree download / upload (tests, checkpointing), grown on demand
+static int ensure_stage(sgo_engine *e, int blocks)
+{
+    if (e->stage_blocks >= blocks) return 0;
+    if (e->stage) cudaFree(e->stage);
+    e->stage = nullptr; e->stage_blocks = 0;
+    SGO_CUDA_OK(e, cudaMalloc(&e->stage, sizeof(NodeBlock) * (size_t)blocks));
+    e->stage_blocks = blocks;
+    return 0;
+}
+
 extern "C" int sgo_tree_download_sync(sgo_engine *e, int32_t tree, void *h_blocks, int32_t max_blocks, void *h_meta, double *h_root_p64)
 {
     if (tree < 0 || tree >= e->G * e->T) return sgo_fail(e, "tree index out of range");
     TreeMeta m;
     SGO_CUDA_OK(e, cudaDeviceSynchronize());
     SGO_CUDA_OK(e, cudaMemcpy(&m, e->meta + tree, sizeof(TreeMeta), cudaMemcpyDeviceToHost));
-    if (h_meta) memcpy(h_meta, &m, sizeof(TreeMeta));
-    int n = m.n_blocks < max_blocks ? m.n_blocks : max_blocks;
-    if (h_blocks && n > 0)
-        SGO_CUDA_OK(e, cudaMemcpy(h_blocks, tree_arena(e->arena, e->NB, tree, m.side), sizeof(NodeBlock) * n, cudaMemcpyDeviceToHost));
+    int n = 0;
+    if (h_blocks && m.valid && max_blocks > 0) {
+        int want = m.n_blocks < max_blocks ? m.n_blocks : max_blocks;
+        int rc = ensure_stage(e, want);
+        if (rc) return rc;
+        k_tree_export<<<1, 32>>>(sgo_pool(e), e->meta, tree, e->stage, want, e->counters + 3);
+        SGO_LAUNCHED(e);
+        SGO_CUDA_OK(e, cudaMemcpy(&n, e->counters + 3, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (n < 0) n = -n;                                    // truncated at max_blocks
+        if (n > 0) SGO_CUDA_OK(e, cudaMemcpy(h_blocks, e->stage, sizeof(NodeBlock) * (size_t)n, cudaMemcpyDeviceToHost));
+    }
+    if (h_meta) { m.root = 0; memcpy(h_meta, &m, sizeof(TreeMeta)); }    // in the exported form the root is block 0
     if (h_root_p64)
         SGO_CUDA_OK(e, cudaMemcpy(h_root_p64, e->root_p64 + (size_t)tree * SGO_APAD, sizeof(double) * SGO_APAD, cudaMemcpyDeviceToHost));
     return 0;
@@ -737,18 +919,30 @@ extern "C" int sgo_tree_download_sync(sgo_engine *e, int32_t tree, void *h_block
 extern "C" int sgo_tree_upload_sync(sgo_engine *e, int32_t tree, const void *h_blocks, int32_t n_blocks, const void *h_meta, const double *h_root_p64)
 {
     if (tree < 0 || tree >= e->G * e->T) return sgo_fail(e, "tree index out of range");
-    if (n_blocks > e->NB) return sgo_fail(e, "tree larger than the arena");
+    if (n_blocks < 0 || n_blocks > e->pool_blocks) return sgo_fail(e, "tree larger than the node pool");
     TreeMeta m;
     memcpy(&m, h_meta, sizeof(TreeMeta));
-    m.n_blocks = n_blocks;
     SGO_CUDA_OK(e, cudaDeviceSynchronize());
-    TreeMeta cur;
-    SGO_CUDA_OK(e, cudaMemcpy(&cur, e->meta + tree, sizeof(TreeMeta), cudaMemcpyDeviceToHost));
-    m.side = cur.side;
-    if (n_blocks > 0)
-        SGO_CUDA_OK(e, cudaMemcpy(tree_arena(e->arena, e->NB, tree, m.side), h_blocks, sizeof(NodeBlock) * n_blocks, cudaMemcpyHostToDevice));
+    // whatever the slot held goes back to the pool first
+    int g = tree / e->T, t = tree % e->T;
+    int32_t *sel = nullptr, *mask = nullptr;
+    SGO_CUDA_OK(e, cudaMalloc(&sel, sizeof(int32_t) * e->G * 2));
+    mask = sel + e->G;
+    SGO_CUDA_OK(e, cudaMemset(sel, 0, sizeof(int32_t) * e->G * 2));
+    int32_t one = 1;
+    SGO_CUDA_OK(e, cudaMemcpy(sel + g, &t, sizeof(int32_t), cudaMemcpyHostToDevice));
+    SGO_CUDA_OK(e, cudaMemcpy(mask + g, &one, sizeof(int32_t), cudaMemcpyHostToDevice));
+    k_tree_free<<<warp_grid(e->G), TREE_WARPS * 32>>>(e->G, e->T, sgo_pool(e), e->meta, mask, sel);
+    SGO_LAUNCHED(e);
+    SGO_CUDA_OK(e, cudaDeviceSynchronize());
+    cudaFree(sel);
+    int rc = ensure_stage(e, n_blocks > 0 ? n_blocks : 1);
+    if (rc) return rc;
+    if (n_blocks > 0) SGO_CUDA_OK(e, cudaMemcpy(e->stage, h_blocks, sizeof(NodeBlock) * (size_t)n_blocks, cudaMemcpyHostToDevice));
+    k_tree_import<<<1, 32>>>(sgo_pool(e), e->meta, tree, e->stage, n_blocks, m, e->err_flags);
+    SGO_LAUNCHED(e);
     if (h_root_p64)
         SGO_CUDA_OK(e, cudaMemcpy(e->root_p64 + (size_t)tree * SGO_APAD, h_root_p64, sizeof(double) * SGO_APAD, cudaMemcpyHostToDevice));
-    SGO_CUDA_OK(e, cudaMemcpy(e->meta + tree, &m, sizeof(TreeMeta), cudaMemcpyHostToDevice));
+    SGO_CUDA_OK(e, cudaDeviceSynchronize());
     return 0;
 }

@@ -13,9 +13,9 @@ NODEBLOCK_DTYPE = np.dtype([('prior', 'f4', 384), ('n', 'i4', 384), ('w', 'f4', 
                             ('exist', 'u4', 12), ('busy', 'u4', 12), ('parent_block', 'i4'), ('parent_slot', 'i4'),
                             ('pad', 'i4', 6)])
 assert NODEBLOCK_DTYPE.itemsize == 6272
-META_FIELDS = ('side', 'n_blocks', 'valid', 'root_f64', 'root_count', 'root_value', 'overflow', 'pad')
+META_FIELDS = ('root', 'n_blocks', 'valid', 'root_f64', 'root_count', 'root_value', 'overflow', 'pad')
 
-ERR_BITS = {1: "make_play on an occupied point (play.py:233 assert)", 2: "MCTS node arena exhausted",
+ERR_BITS = {1: "make_play on an occupied point (play.py:233 assert)", 2: "MCTS node pool exhausted (raise arena_blocks)",
             4: "selector found no child (reference would raise)", 8: "tree deeper than SGO_MAXDEPTH"}
 
 
@@ -158,6 +158,27 @@ class Engine(object):
     def tree_reset(self):
         self._ck(self.lib.sgo_tree_reset(self.h, self._stream()))
 
+    def tree_free(self, game_mask):
+        m = self.dev(game_mask, torch.int32)
+        assert m.numel() == self.G
+        self._ck(self.lib.sgo_tree_free(self.h, self._p(m), self._stream()))
+
+    def games_restart(self, game_mask):
+        """game_init + drop the trees of the flagged games (a slot starting its next game)."""
+        m = self.dev(game_mask, torch.int32)
+        assert m.numel() == self.G
+        self._ck(self.lib.sgo_games_restart(self.h, self._p(m), self._stream()))
+
+    def tree_sizes(self):
+        out = torch.empty((self.G, self.T), dtype=torch.int32, device=self.device)
+        self._ck(self.lib.sgo_tree_sizes(self.h, self._p(out), self._stream()))
+        return out
+
+    def pool_stats(self):
+        out = (C.c_int64 * 4)()
+        self._ck(self.lib.sgo_pool_stats_sync(self.h, out, self._stream()))
+        return dict(capacity=int(out[0]), free=int(out[1]), min_free=int(out[2]), failed_allocs=int(out[3]))
+
     def tree_new(self, policy, noise=None, eps=0.25, force=False, tree_sel=None):
         p = self.dev(policy, torch.float32)
         assert p.numel() == self.G * self.A
@@ -257,10 +278,14 @@ class Engine(object):
         return out
 
     def download_tree(self, tree=0):
-        blocks = np.zeros(self.NB, dtype=NODEBLOCK_DTYPE)
+        """-> (blocks, meta, root_p64) in canonical form: block 0 is the root, the rest in breadth-first slot order,
+        child / parent links index into `blocks` (the pool ids a tree occupies are an allocation detail)."""
         meta = np.zeros(8, dtype=np.int32)
         p64 = np.zeros(384, dtype=np.float64)
-        self._ck(self.lib.sgo_tree_download_sync(self.h, tree, blocks.ctypes.data_as(C.c_void_p), self.NB,
+        self._ck(self.lib.sgo_tree_download_sync(self.h, tree, None, 0, meta.ctypes.data_as(C.c_void_p), None))
+        nb = max(1, int(meta[1]))
+        blocks = np.zeros(nb, dtype=NODEBLOCK_DTYPE)
+        self._ck(self.lib.sgo_tree_download_sync(self.h, tree, blocks.ctypes.data_as(C.c_void_p), nb,
                                                  meta.ctypes.data_as(C.c_void_p), p64.ctypes.data_as(C.c_void_p)))
         m = dict(zip(META_FIELDS, meta.tolist()))
         m['root_value'] = float(meta[5:6].view(np.float32)[0])
