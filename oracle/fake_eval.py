@@ -17,6 +17,16 @@ def _mix(h):
     return h ^ (h >> np.uint64(33))
 
 
+def hash_rows(a):
+    """uint64 hash of every row of a 2-D unsigned integer array (packed states, legality masks): lets a fixture
+    pin thousands of plies without storing them."""
+    a = np.ascontiguousarray(a)
+    a = a.reshape(a.shape[0], -1).astype(np.uint64)
+    w = _mix(np.arange(1, a.shape[1] + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15))
+    with np.errstate(over='ignore'):
+        return _mix((_mix(a + w[None, :]) * w[None, :]).sum(axis=1, dtype=np.uint64) + np.uint64(a.shape[1]))
+
+
 def board_key(boards):
     """boards [n,S,S,17] (any numeric dtype) -> uint64[n] position hash."""
     b = np.asarray(boards)

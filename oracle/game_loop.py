@@ -219,3 +219,25 @@ def play_game_async(model1_indicator, model2_indicator, energy, stop_exploration
         model1_isblack = gd['modelB'] is t1
         gd['winner_model'] = gd['modelB_name'] if ((gd['winner'] == 1) == model1_isblack) else gd['modelW_name']
     return gd
+
+
+def self_play(model, n_games, mcts_simulations, lottery, percent, allowed_error, stop_exploration, size=19,
+              mcts_batch_size=100, rng=None, komi=5.5):
+    """self_play.py:343-378 (and, with the directory handling stripped, model_self_play :293-340 and
+    NoModelSelfPlayWorker.run selfplay_worker.py:76-112): n games one after the other with the resignation
+    calibration.  lottery() stands for the `random()` of the per-game lottery; rng feeds play_game."""
+    games_data = []
+    current_resign = None
+    min_values = []
+    for game in range(n_games):
+        resign = current_resign if lottery() > percent else None
+        gd = play_game(model, model, mcts_simulations, stop_exploration, self_play=True, resign_model1=resign,
+                       resign_model2=resign, size=size, mcts_batch_size=mcts_batch_size, rng=rng, komi=komi)
+        if resign is None:
+            mv = gd['moves'][::2] if gd['winner'] == 1 else gd['moves'][1::2]
+            min_values.append(min(m['value'] for m in mv))
+            idx = int(allowed_error * len(min_values))
+            if idx > 0:
+                current_resign = min_values[idx]
+        games_data.append(gd)
+    return games_data

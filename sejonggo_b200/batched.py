@@ -124,6 +124,10 @@ class BatchedGames(object):
         self.after_search = None      # parity hook: called as after_search(self, tree_sel) between the search and the move pick
         # with GPU towers the whole search step runs inside the library (sgo_selfplay_step)
         self.native_step = native_step and self.fast and all(hasattr(ev, "attach") for ev in self.ev)
+        self.store = None             # records.RecordStore when record_boards == 'device' (rows stay in HBM for the gather)
+        if record_boards == 'device':
+            from .records import RecordStore
+            self.store = RecordStore(size, max(4096, 64 * n_games), self.eng.device)
         self.trees_dropped = 0        # trees given up for lack of pool room (_ensure_pool_room)
         self.sim_count = 0            # leaves expanded + backed up (the north-star "simulations")
         self.eval_count = 0
@@ -389,6 +393,9 @@ class BatchedGames(object):
         for g in slots:
             gd = self._game_data(int(g), sc[g])
             gid = int(self.slot_game[g])
+            if self.store is not None:
+                from .records import footer_row
+                self.store.append_host_rows(footer_row(self.S, gid, gd))
             self.results[gid] = gd
             self.slot_game[g] = -1
             self.moves_rec[g] = []
@@ -474,7 +481,8 @@ class BatchedGames(object):
         u01 = None
         prior_h = None
         packed_rec = record and self.record_boards == 'packed'
-        if record and not packed_rec:
+        device_rec = record and self.record_boards == 'device'
+        if record and not packed_rec and not device_rec:
             prior, count, _ = e.child_stats(tree_sel, want=("prior", "count"))
             prior_h = prior.cpu().numpy()                       # policy_target = root priors (Q14)
             self.d2h_bytes += prior_h.nbytes
@@ -483,7 +491,7 @@ class BatchedGames(object):
             u01 = np.array([self.rngs[0].uniform() for _ in range(G)], np.float64)    # device-side sampling
             self.h2d_bytes += u01.nbytes
         elif explore.any():
-            if not record or packed_rec:
+            if not record or packed_rec or device_rec:
                 _, count, _ = e.child_stats(tree_sel, want=("count",))
             count_h = count.cpu().numpy()
             forced = np.full(G, -1, np.int32)
@@ -509,6 +517,9 @@ class BatchedGames(object):
             boards_h = rec_h[:, :PW]
             prior_h = rec_h[:, PW + 3:PW + 3 + A].view(np.float32)
             self.d2h_bytes += rec_h.nbytes - boards_h.nbytes
+        elif device_rec:
+            # the rows stay in HBM (records.RecordStore) until they are gathered; the host keeps what the game flow needs
+            self.store.append_plies(e.records_pack(tree_sel, index_dev, value), act_idx, self.slot_game[act_idx], move_n[act_idx])
         if boards_h is not None:
             self.d2h_bytes += boards_h.nbytes
         apply = np.full(G, -1, np.int32)
@@ -519,7 +530,8 @@ class BatchedGames(object):
             if record:
                 self.moves_rec[g].append(dict(
                     board=None if boards_h is None else (boards_h[g:g + 1].copy() if self.record_boards == 'full' else boards_h[g].copy()),
-                    policy=prior_h[g].copy(), value=value_h[g], move=(x, y), move_n=int(move_n[g]), player=int(self.player[g])))
+                    policy=None if prior_h is None else prior_h[g].copy(), value=value_h[g], move=(x, y), move_n=int(move_n[g]),
+                    player=int(self.player[g])))
             if self.skipped_last[g] and y == S:
                 self.end_reason[g] = "BOTH_PASSED"
                 active[g] = False

@@ -2,8 +2,10 @@
 with NO collective on the per-simulation path.  NCCL (torch.distributed) is used for the
 two real exchanges only, replacing the reference's scp of .h5 models and zipped game
 directories (slave_coordinator.py:45-82):
-  * broadcast_params  — rank 0's weights to every rank at a model change
-  * gather_records    — packed game records to rank 0 at game end (counts, then payload)
+  * broadcast_model — rank 0's network to every rank at a model change: ONE blob of folded weights (tower convs in
+                      bf16, 48 MB at 20 blocks), device to device
+  * gather_rows     — the packed game records (records.py rows: board, move, value, policy_target per ply) to rank 0:
+                      row counts by all_gather, then the payloads device to device
 """
 import os
 import numpy as np
@@ -30,77 +32,84 @@ def shard_games(n_games, rank, world):
     return np.arange(rank, n_games, world)
 
 
-def _flat_items(params):
-    for k in sorted(k for k in params if k != 'meta'):
-        v = params[k]
-        if isinstance(v, dict):
-            for kk in sorted(v):
-                yield (k, kk), v[kk]
-        else:
-            yield (k, None), v
+def _world():
+    return dist.get_world_size() if dist.is_initialized() else 1
 
 
-def broadcast_params(params, src=0, device=None):
-    """In-place broadcast of a model.init_params-style dict (one flat fp32 buffer)."""
-    if not dist.is_initialized() or dist.get_world_size() == 1:
-        return params
-    items = list(_flat_items(params))
-    flat = torch.cat([t.reshape(-1).float() for _, t in items])
-    if device is not None:
-        flat = flat.to(device)
-    dist.broadcast(flat, src=src)
-    flat = flat.cpu()
-    o = 0
-    for (k, kk), t in items:
-        n = t.numel()
-        new = flat[o:o + n].reshape(t.shape).to(t.dtype)
-        if kk is None:
-            params[k] = new
-        else:
-            params[k][kk] = new
-        o += n
-    return params
+HEADER_BYTES = 256
 
 
-def gather_records(payload, dst=0, device=None):
-    """payload: 1-D uint8 tensor of this rank's packed records.  Two-phase gather: byte counts
-    (all_gather), then a gather of the padded payloads to dst.  Returns a list of per-rank tensors on dst, else None."""
-    if not dist.is_initialized() or dist.get_world_size() == 1:
-        return [payload]
+def broadcast_model(model, src=0, device=None, max_positions=None):
+    """Every rank returns a TowerModel with rank `src`'s weights and name.  `model` is only read on `src` (others may
+    pass None).  Two collectives: a 256-byte header (name, board size, blocks), then the weight blob, which is
+    packed on the device on `src` and consumed in place on the others — no host copy on either side."""
+    from . import model as M
+    if _world() == 1:
+        return model
+    rank = dist.get_rank()
+    dev = torch.device(device) if device is not None else torch.device("cpu")
+    head = torch.zeros(HEADER_BYTES, dtype=torch.uint8, device=dev)
+    if rank == src:
+        nm = model.name.encode("utf-8")[:HEADER_BYTES - 16]
+        h = np.zeros(HEADER_BYTES, np.uint8)
+        h[:4] = np.array([model.size], np.int32).view(np.uint8)
+        h[4:8] = np.array([model.n_blocks], np.int32).view(np.uint8)
+        h[8:12] = np.array([len(nm)], np.int32).view(np.uint8)
+        h[16:16 + len(nm)] = np.frombuffer(nm, np.uint8)
+        head.copy_(torch.from_numpy(h))
+    dist.broadcast(head, src=src)
+    h = head.cpu().numpy()
+    size, n_blocks, ln = (int(x) for x in h[:12].view(np.int32))
+    name = bytes(h[16:16 + ln]).decode("utf-8")
+    _, total = M.blob_layout(size, n_blocks)
+    blob = model.blob(dev) if rank == src else torch.empty(total, dtype=torch.uint8, device=dev)
+    dist.broadcast(blob, src=src)
+    if rank == src:
+        return model
+    mp = max_positions or (model.max_positions if model is not None else 8192)
+    return M.TowerModel(name, folded=(M.unpack_blob(blob, size, n_blocks), size, n_blocks), max_positions=mp)
+
+
+def blob_bytes(model):
+    from . import model as M
+    return M.blob_layout(model.size, model.n_blocks)[1]
+
+
+def gather_rows(rows, dst=0):
+    """rows: int32 [n][RW] tensor of this rank's record rows (on the device the process group communicates on).
+    Returns on `dst` the list of every rank's rows (tensors on that device), elsewhere None.  Row counts travel by
+    all_gather; each payload by ONE exact-size send/recv (NCCL: device to device over NVLink)."""
+    if _world() == 1:
+        return [rows]
     world, rank = dist.get_world_size(), dist.get_rank()
-    dev = device if device is not None else payload.device
-    count = torch.tensor([payload.numel()], dtype=torch.int64, device=dev)
-    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    RW = int(rows.shape[1])
+    count = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
+    counts = [torch.zeros(1, dtype=torch.int64, device=rows.device) for _ in range(world)]
     dist.all_gather(counts, count)
-    mx = int(max(int(c.item()) for c in counts))
-    buf = torch.zeros(mx, dtype=torch.uint8, device=dev)
-    buf[:payload.numel()] = payload.to(dev)
-    bufs = [torch.zeros(mx, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == dst else None
-    dist.gather(buf, gather_list=bufs, dst=dst)          # payloads travel to dst only (NCCL: grouped send/recv)
-    if rank != dst:
-        return None
-    return [b[:int(c.item())].cpu() for b, c in zip(bufs, counts)]
+    counts = [int(c.item()) for c in counts]
+    if rank == dst:
+        out, reqs = [], []
+        for r in range(world):
+            if r == dst:
+                out.append(rows)
+                continue
+            buf = torch.empty((counts[r], RW), dtype=torch.int32, device=rows.device)
+            out.append(buf)
+            if counts[r]:
+                reqs.append(dist.irecv(buf, src=r))
+        for q in reqs:
+            q.wait()
+        return out
+    if rows.shape[0]:
+        dist.isend(rows.contiguous(), dst=dst).wait()
+    return None
 
 
-def pack_records(games):
-    """game_data list -> one uint8 tensor (move lists + results; boards are replayable from moves)."""
-    out = []
-    for g in games:
-        mv = np.array([m['move'][0] + 1000 * m['move'][1] for m in g['moves']], np.int32)
-        head = np.array([len(mv), -1 if g['winner'] is None else g['winner']], np.int32)
-        out.append(head.view(np.uint8))
-        out.append(mv.view(np.uint8))
-    if not out:
-        return torch.zeros(0, dtype=torch.uint8)
-    return torch.from_numpy(np.concatenate(out).copy())
-
-
-def unpack_records(buf):
-    a = buf.numpy().view(np.int32)
-    games, o = [], 0
-    while o < len(a):
-        n, w = int(a[o]), int(a[o + 1])
-        mv = a[o + 2:o + 2 + n]
-        games.append(dict(moves=[(int(m % 1000), int(m // 1000)) for m in mv], winner=None if w < 0 else w))
-        o += 2 + n
-    return games
+def gather_per_rank(values, device=None):
+    """Small per-rank diagnostics (a list of floats) from every rank: -> float64 [world][len(values)] on all ranks."""
+    t = torch.tensor(values, dtype=torch.float64, device=device)
+    if _world() == 1:
+        return t.reshape(1, -1).cpu().numpy()
+    outs = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(outs, t)
+    return torch.stack(outs).cpu().numpy()

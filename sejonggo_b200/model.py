@@ -104,16 +104,76 @@ def folded_arrays(p):
     return out
 
 
+# ---- the weights as ONE blob: what a rank needs to play (BN folded, tower convs in bf16), in the order of
+# sgo_tower_weights.  SURVEY §8e: this is what rank 0 broadcasts over NCCL at a model change (48 MB at 20 blocks)
+# instead of the reference's scp of a Keras .h5 (slave_coordinator.py:45-63).
+BLOB_KEYS = ("stem_w", "stem_b", "conv_w", "conv_b", "pol_conv_w", "pol_conv_b", "pol_fc_w", "pol_fc_b",
+             "val_conv_w", "val_conv_b", "val_fc1_w", "val_fc1_b", "val_fc2_w", "val_fc2_b")
+BLOB_ALIGN = 256
+
+
+def blob_layout(size, n_blocks):
+    """-> ([(key, dtype, shape, byte offset)], total bytes); a function of the architecture only, so every rank
+    computes it without communication."""
+    C_, W, A = CHANNELS, size - 2, size * size + 1
+    F = 2 * W * W
+    shapes = dict(stem_w=(3, 3, 17, C_), stem_b=(C_,), conv_w=(2 * n_blocks, 3, 3, C_, C_), conv_b=(2 * n_blocks, C_),
+                  pol_conv_w=(C_, 2), pol_conv_b=(2,), pol_fc_w=(F, A), pol_fc_b=(A,), val_conv_w=(C_, 2), val_conv_b=(2,),
+                  val_fc1_w=(F, 256), val_fc1_b=(256,), val_fc2_w=(256,), val_fc2_b=(1,))
+    out, o = [], 0
+    for k in BLOB_KEYS:
+        dt = torch.bfloat16 if k == "conv_w" else torch.float32
+        n = int(np.prod(shapes[k])) * (2 if dt == torch.bfloat16 else 4)
+        out.append((k, dt, shapes[k], o))
+        o = (o + n + BLOB_ALIGN - 1) // BLOB_ALIGN * BLOB_ALIGN
+    return out, o
+
+
+def pack_blob(folded, size, n_blocks, device):
+    layout, total = blob_layout(size, n_blocks)
+    blob = torch.zeros(total, dtype=torch.uint8, device=device)
+    for k, dt, shape, o in layout:
+        t = folded[k].to(device=device, dtype=dt).contiguous().reshape(-1)
+        if t.numel():
+            blob[o:o + t.numel() * t.element_size()] = t.view(torch.uint8)
+    return blob
+
+
+def unpack_blob(blob, size, n_blocks):
+    """Typed views into the blob (no copies): the dict folded_arrays() would give."""
+    layout, total = blob_layout(size, n_blocks)
+    assert blob.numel() == total and blob.dtype == torch.uint8
+    out = {}
+    for k, dt, shape, o in layout:
+        n = int(np.prod(shape)) * (2 if dt == torch.bfloat16 else 4)
+        out[k] = blob[o:o + n].view(dt).reshape(shape) if n else torch.zeros(shape, dtype=dt, device=blob.device)
+    return out
+
+
 class TowerModel(object):
     is_sgo_evaluator = True
 
-    def __init__(self, name="model_1", params=None, size=None, n_blocks=None, seed=0, max_positions=8192):
+    def __init__(self, name="model_1", params=None, size=None, n_blocks=None, seed=0, max_positions=8192, folded=None):
+        """params: a Keras-layout dict (init_params / load_params); or folded=(dict from unpack_blob, size, n_blocks) for a
+        model received as a blob (it can play, but has no fp32 parameters to save)."""
         self.name = name
-        self.params = params if params is not None else init_params(size, n_blocks, seed)
-        self.size = self.params['meta']['size']
+        if folded is not None:
+            self._folded, self.size, self.n_blocks = folded
+            self.params = None
+        else:
+            self.params = params if params is not None else init_params(size, n_blocks, seed)
+            self.size, self.n_blocks = self.params['meta']['size'], self.params['meta']['n_blocks']
+            self._folded = None
         self.max_positions = max_positions
-        self._folded = None
         self._host_engine = None
+
+    def folded(self):
+        if self._folded is None:
+            self._folded = folded_arrays(self.params)
+        return self._folded
+
+    def blob(self, device):
+        return pack_blob(self.folded(), self.size, self.n_blocks, device)
 
     # ---- engine-side protocol ----------------------------------------------------
     def attach(self, engine, slot=0, max_positions=None):
@@ -123,10 +183,8 @@ class TowerModel(object):
             return
         if engine.S != self.size:
             raise EngineError("model is for %dx%d boards, engine is %dx%d" % (self.size, self.size, engine.S, engine.S))
-        if self._folded is None:
-            self._folded = folded_arrays(self.params)
-        dev = {k: v.to(engine.device) for k, v in self._folded.items()}
-        w = _abi.SgoTowerWeights(n_blocks=self.params['meta']['n_blocks'], channels=CHANNELS, size=self.size)
+        dev = {k: v.to(engine.device).contiguous() for k, v in self.folded().items()}
+        w = _abi.SgoTowerWeights(n_blocks=self.n_blocks, channels=CHANNELS, size=self.size)
         for k, v in dev.items():
             setattr(w, k, v.data_ptr())
         mp = max_positions or self.max_positions
@@ -169,6 +227,8 @@ class TowerModel(object):
 
     def save(self, path):
         """Keras model.save (evaluator.py:20, model.py:117-119) for the .npz weight files."""
+        if self.params is None:
+            raise EngineError("a model received as a folded blob has no fp32 parameters to save")
         save_params(path, self.params, self.name)
 
     # ---- reference protocol (self_play.py:70,187) ----------------------------------

@@ -71,10 +71,11 @@ class ResignationCalibrator(object):
             self.current_resign = self.min_values[idx]
 
 
-def self_play(model, n_games, mcts_simulations, concurrent=None, record_boards='packed', save=True, rand=random, **kw):
+def self_play(model, n_games, mcts_simulations, concurrent=None, record_boards='packed', save=True, rand=random,
+              calibrator=None, **kw):
     """self_play.py:343-378: n self-play games with the resignation calibration, each saved through
     save_game_data(model.name, game, game_data) as it finishes."""
-    cal = ResignationCalibrator(rand=rand)
+    cal = calibrator or ResignationCalibrator(rand=rand)
     size = kw.get('size') or conf['SIZE']
 
     def on_end(game, gd):
@@ -87,7 +88,7 @@ def self_play(model, n_games, mcts_simulations, concurrent=None, record_boards='
                       on_game_start=cal.start, on_game_end=on_end, **kw)
 
 
-def model_self_play(model, one_game_only=-1, concurrent=None, record_boards='packed', rand=random, **kw):
+def model_self_play(model, one_game_only=-1, concurrent=None, record_boards='packed', rand=random, calibrator=None, **kw):
     """self_play.py:293-340: conf['N_GAMES'] games of conf['MCTS_SIMULATIONS'], skipping games whose directory
     SELF_PLAY_DIR/<model>/game_%05d already exists (resume; a directory is claimed by creating it), each saved
     through save_self_play_data as it finishes."""
@@ -95,7 +96,7 @@ def model_self_play(model, one_game_only=-1, concurrent=None, record_boards='pac
     size = kw.get('size') or conf['SIZE']
     todo = [g for g in range(conf['N_GAMES']) if (one_game_only < 0 or g == one_game_only)
             and not os.path.isdir(os.path.join(root, "game_%05d" % g))]
-    cal = ResignationCalibrator(rand=rand)
+    cal = calibrator or ResignationCalibrator(rand=rand)
 
     def on_start(i):
         try:

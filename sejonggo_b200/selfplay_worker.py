@@ -20,7 +20,7 @@ from .sgfsave import save_self_play_data
 
 
 def run_selfplay(n_games=None, concurrent=None, energy=None, device=0, size=None, record_boards='packed', games=None,
-                 rand=random, **kw):
+                 rand=random, calibrator=None, **kw):
     """Plays the still-unclaimed games among `games` (default range(N_GAMES)); returns the game numbers saved."""
     n_games = conf['N_GAMES'] if n_games is None else n_games
     concurrent = concurrent or conf['CONCURRENT_GAMES']
@@ -30,7 +30,7 @@ def run_selfplay(n_games=None, concurrent=None, energy=None, device=0, size=None
     todo = [g for g in (range(n_games) if games is None else games) if not os.path.isdir(os.path.join(root, "game_%05d" % g))]
     if not todo:
         return []
-    cal = ResignationCalibrator(rand=rand)
+    cal = calibrator or ResignationCalibrator(rand=rand)
     saved = []
 
     def on_start(i):

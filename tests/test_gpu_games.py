@@ -23,7 +23,8 @@ def test_game_fixture(name):
     z = np.load(os.path.join(GOLDEN, name))
     S, mode, batch, sims, seed = int(z["size"]), str(z["mode"]), int(z["batch"]), int(z["sims"]), int(z["seed"])
     kw = game_kwargs(z)
-    rng = gl.ReplayRng(coin=z["coin"], noise=z["noise"], choice=z["choice"])
+    live = "live_sym" in z.files and int(z["live_sym"])
+    rng = gl.ReplayRng(coin=z["coin"], noise=z["noise"], choice=z["choice"], symmetry=z["symmetry"] if live else None)
     kind = str(z["evalkind"]) if "evalkind" in z.files else "fake"
     m1 = FakeModel("model_1", salt=seed, sharp=True, kind=kind)
     m2 = m1 if kw['self_play'] else FakeModel("model_2", salt=seed + 1, sharp=True, kind=kind)
@@ -32,18 +33,22 @@ def test_game_fixture(name):
         conf.update(SIZE=S, MCTS_BATCH_SIZE=batch, ENERGY=batch, MCTS_SIMULATIONS=sims, KOMI=5.5)
         if mode == 'a':
             gd = sp.play_game(m1, m2, sims, kw['stop_exploration'], kw['self_play'], kw['num_moves'],
-                              kw['resign_model1'], kw['resign_model2'], rng=rng, use_symmetry=False)
+                              kw['resign_model1'], kw['resign_model2'], rng=rng, use_symmetry=bool(live))
             calls = m1.calls + [-1] + (m2.calls if m2 is not m1 else [])
             assert calls == list(z["calls"])
         else:
             pq.register_models(best=m1, latest=m2)
             i1, i2 = ("BEST", "BEST") if kw['self_play'] else ("BEST", "LATEST")
+            if live:            # the *_SYM tags: one symmetry per request, LATEST_SYM served by the best network (Q21)
+                i1, i2 = ("BEST_SYM", "BEST_SYM") if kw['self_play'] else ("BEST_SYM", "LATEST_SYM")
             gd = nsp.play_game_async(i1, i2, batch, kw['stop_exploration'], 0, kw['self_play'], kw['num_moves'],
                                      kw['resign_model1'], kw['resign_model2'], rng=rng)
     finally:
         conf.clear()
         conf.update(old)
     check_game(gd, z)
+    if live:
+        assert len(rng._sym) == 0
 
 
 def test_batched_games_match_single_games():
@@ -254,6 +259,38 @@ def test_gtp_engine_matches_oracle_search():
             assert np.array_equal(g.board, board), cmd
         assert g.parse_command("clear_board") == "=\n\n"
         assert np.array_equal(g.board, o.game_init(S)[0])
+    finally:
+        conf.clear()
+        conf.update(old)
+
+
+def test_main_selfplay_launcher_single_rank(tmp_path, capsys):
+    """main_selfplay.main (main_selfplay.py:9-29) in one process: loads / creates the best model, plays the unplayed
+    games with slot refill, keeps the record rows on the device, "gathers" them (world 1) and writes the reference's
+    directory tree; a second round finds no new best model and stops; a re-run skips the games already on disk."""
+    from sejonggo_b200 import main_selfplay as ms, model
+    from sejonggo_b200.conf import conf
+    old = dict(conf)
+    try:
+        conf.update(SIZE=9, N_RESIDUAL_BLOCKS=1, MCTS_SIMULATIONS=16, ENERGY=8, MCTS_BATCH_SIZE=8, STOP_EXPLORATION=2,
+                    SELF_PLAY_DIR=str(tmp_path / "sp"), MODEL_DIR=str(tmp_path / "models"), N_GAMES=7, CONCURRENT_GAMES=3,
+                    RESIGNATION_PERCENT=1.0)
+        os.makedirs(tmp_path / "sp" / "model_1" / "game_00002")               # already played elsewhere
+        ms.main(["--games", "7", "--concurrent", "3", "--sims", "16", "--mode", "b", "--num-moves", "5", "--gather-every", "2"])
+        out = capsys.readouterr().out
+        assert "SELF-PLAYING BEST MODEL  model_1" in out and "No new best model for self-playing. Stopping.." in out
+        assert "6 games saved" in out
+        root = tmp_path / "sp" / "model_1"
+        for g in (0, 1, 3, 4, 5, 6):
+            moves = sorted(os.listdir(root / ("game_%05d" % g)))
+            assert moves and moves[0] == "move_000" and len(moves) <= 5
+            z = np.load(root / ("game_%05d" % g) / "move_000" / "sample.npz")
+            assert z["board"].shape == (1, 9, 9, 17) and float(z["board"][..., :16].sum()) == 0.0 and float(z["board"][0, 0, 0, 16]) == 1.0
+            assert z["policy_target"].shape == (82,) and abs(float(z["policy_target"].sum()) - 1.0) < 0.05
+            assert float(z["value_target"]) in (1.0, -1.0)
+        assert os.listdir(root / "game_00002") == []                           # the claimed one was left alone
+        ms.main(["--games", "7", "--concurrent", "3", "--sims", "16", "--mode", "a", "--num-moves", "5", "--max-rounds", "1"])
+        assert "0 games saved" in capsys.readouterr().out                      # resume: nothing left to play
     finally:
         conf.clear()
         conf.update(old)

@@ -53,6 +53,37 @@ def test_make_play_occupied_asserts():
         play.make_play(3, 3, b)
 
 
+def test_rules_64_long_19x19_games_lockstep():
+    """64 reference-played 19x19 games (several reach the 722-ply cap; suicides and ko retakes executed) advanced in
+    lock-step on the device: packed state and legality mask of every game at every ply against the reference's row
+    hashes, and the final area scores."""
+    from oracle.fake_eval import hash_rows
+    z = np.load(os.path.join(GOLDEN, "ruleshash_s19_64.npz"))
+    S = int(z["size"])
+    offs, moves = z["move_offsets"], z["moves"].astype(np.int32)
+    G = len(offs) - 1
+    lens = np.diff(offs)
+    srow = np.concatenate([[0], np.cumsum(lens + 1)])[:-1]
+    e = _engine(size=S, n_games=G, max_leaves=1, arena_blocks=2)
+    e.reset()
+    checked = 0
+    for t in range(int(lens.max()) + 1):
+        sh = hash_rows(e.export_packed(0).cpu().numpy().view(np.uint32))
+        mh = hash_rows(e.legal_masks().cpu().numpy())
+        live = np.nonzero(t <= lens)[0]
+        assert np.array_equal(sh[live], z["state_hash"][srow[live] + t]), t
+        assert np.array_equal(mh[live], z["mask_hash"][srow[live] + t]), t
+        checked += len(live)
+        mv = np.where(t < lens, moves[np.minimum(offs[:-1] + t, len(moves) - 1)], -1).astype(np.int32)
+        e.apply_moves(mv)
+    assert checked == len(z["state_hash"]) > 20000
+    sc = e.score().cpu().numpy()
+    for g in range(G):
+        w, b, wh = z["results"][g]
+        assert (sc[g, 0], sc[g, 1], sc[g, 2] + 5.5) == (w, b, wh), g
+    e.check_errors()
+
+
 @pytest.mark.parametrize("size", [5, 9, 19])
 def test_rules_fixture_lockstep(size):
     z = np.load(os.path.join(GOLDEN, "rules_s%d.npz" % size))

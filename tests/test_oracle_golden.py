@@ -106,7 +106,8 @@ def game_kwargs(z):
 def test_game_fixture(name):
     z = _load(name)
     S, mode, batch, sims, seed = int(z["size"]), str(z["mode"]), int(z["batch"]), int(z["sims"]), int(z["seed"])
-    rng = gl.ReplayRng(coin=z["coin"], noise=z["noise"], choice=z["choice"])
+    live = "live_sym" in z.files and int(z["live_sym"])
+    rng = gl.ReplayRng(coin=z["coin"], noise=z["noise"], choice=z["choice"], symmetry=z["symmetry"] if live else None)
     kw = game_kwargs(z)
     kind = str(z["evalkind"]) if "evalkind" in z.files else "fake"
     if mode == 'a':
@@ -120,6 +121,9 @@ def test_game_fixture(name):
         names = {"BEST_SYM": "model_1", "LATEST_SYM": "model_2"}
 
         def predict(tag, board, sym):
+            if live:        # all 7 symmetries in play; LATEST_SYM is served by the BEST network (Q21)
+                p, v = gl.sym_predict(FakeModel("model_1", salt=seed, sharp=True, kind=kind), board, sym)
+                return p[0], v[0]
             p, v = evaluate_kind(board, salts[tag], True, kind)
             return p[0], v[0]
 
@@ -127,3 +131,57 @@ def test_game_fixture(name):
         gd = gl.play_game_async(i1, i2, batch, process_id=0, size=S, conf_sims=sims, conf_energy=batch,
                                 rng=rng, predict=predict, names=names, **kw)
     check_game(gd, z)
+    if live:
+        assert len(rng._sym) == 0 and len(set(z["symmetry"].tolist())) >= 5      # every recorded draw consumed; most of the 7 maps occurred
+
+
+def _calib_checks(games, z):
+    offs = z["move_offsets"]
+    assert len(games) == int(z["n_games"])
+    S = int(z["size"])
+    for g, gd in enumerate(games):
+        want = z["resign"][g]
+        got = gd['resign_model1']
+        assert (got is None and np.isnan(want)) or (got is not None and np.float32(got) == np.float32(want)), (g, got, want)
+        mv = z["move"][offs[g]:offs[g + 1]]
+        assert [tuple(m['move']) for m in gd['moves']] == [tuple(x) for x in mv.tolist()], g
+        assert np.array_equal(np.array([np.float32(m['value']) for m in gd['moves']], np.float32).view(np.uint32),
+                              z["value"][offs[g]:offs[g + 1]].view(np.uint32)), g
+        assert gd['result'] == str(z["result"][g]) and (-1 if gd['winner'] is None else gd['winner']) == int(z["winner"][g]), g
+
+
+def test_self_play_resignation_calibration_fixture():
+    """self_play.self_play (self_play.py:343-378) run by the unmodified reference with recorded draws: 16 games, the
+    lottery, thresholds appearing from the 4th game on (index into the UNSORTED min_values list) and games that
+    resign — the oracle's restatement reproduces every game and every threshold."""
+    z = _load("selfplay_calib_s5.npz")
+    S, batch, sims, seed = int(z["size"]), int(z["batch"]), int(z["sims"]), int(z["seed"])
+    rng = gl.ReplayRng(coin=z["coin"], noise=z["noise"], choice=z["choice"])
+    lot = list(z["lottery"])
+    games = gl.self_play(FakeModel("model_1", salt=seed, sharp=True), int(z["n_games"]), sims, lambda: lot.pop(0),
+                         float(z["percent"]), float(z["allowed_error"]), int(z["stop_exploration"]), size=S,
+                         mcts_batch_size=batch, rng=rng, komi=float(z["komi"]))
+    _calib_checks(games, z)
+    assert not lot and np.isfinite(z["resign"]).sum() >= 4 and any(str(r).endswith("+R") for r in z["result"])
+
+
+def test_rules_64_long_19x19_games_hashed():
+    """64 games played by the unmodified reference on 19x19 (several run into the 2*S*S = 722-ply cap; suicides
+    and ko retakes included): the oracle's replay reproduces the packed state and the legality mask at every one of
+    the ~25,000 plies (64-bit row hashes) and every final result."""
+    from oracle.fake_eval import hash_rows
+    z = _load("ruleshash_s19_64.npz")
+    S = int(z["size"])
+    offs = z["move_offsets"]
+    lens = np.diff(offs)
+    assert len(lens) == 64 and (lens == 2 * S * S).sum() >= 5 and lens.sum() > 20000
+    pos = 0
+    for g in range(len(lens)):
+        mv = z["moves"][offs[g]:offs[g + 1]].astype(np.int32)
+        w, b, wh, states, masks = o.replay(S, mv, float(z["komi"]))
+        n = len(mv) + 1
+        assert np.array_equal(hash_rows(states), z["state_hash"][pos:pos + n]), g
+        assert np.array_equal(hash_rows(masks), z["mask_hash"][pos:pos + n]), g
+        assert (w, b, wh) == tuple(z["results"][g]), g
+        pos += n
+    assert pos == len(z["state_hash"])
