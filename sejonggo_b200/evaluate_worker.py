@@ -36,10 +36,13 @@ def _claim(latest_name, n_games, limit):
     return claimed
 
 
-def run_evaluation(best_model, latest_model, n_games=None, concurrent=None, mode='a', save_training_data=None, **kw):
+def run_evaluation(best_model, latest_model, n_games=None, concurrent=None, mode='a', save_training_data=None,
+                   reference_q21=False, **kw):
     """Plays the unclaimed games of best vs latest; returns (wins of latest, games played).
     mode 'a' = EvaluateWorker (self_play.play_game), 'b' = NoModelEvaluateWorker (play_game_async
-    with the BEST_SYM / LATEST_SYM tags)."""
+    with the BEST_SYM / LATEST_SYM tags).  In the reference the LATEST_SYM tag is served by the BEST network (Q21),
+    so its mode-B evaluation never plays the candidate; here LATEST_SYM goes to the latest model unless
+    reference_q21=True asks for the reference's behaviour."""
     n_games = n_games or conf['EVALUATE_N_GAMES']
     concurrent = concurrent or conf['CONCURRENT_GAMES']
     if save_training_data is None:
@@ -55,7 +58,11 @@ def run_evaluation(best_model, latest_model, n_games=None, concurrent=None, mode
             games = play_games(best_model, latest_model, len(claimed), conf['MCTS_SIMULATIONS'], stop_exploration=0, **kw)
         else:
             pq.register_models(best=best_model, latest=latest_model)
-            games = play_games_async("BEST_SYM", "LATEST_SYM", len(claimed), conf['ENERGY'], 0, **kw)
+            q21, pq.REFERENCE_Q21 = pq.REFERENCE_Q21, bool(reference_q21)
+            try:
+                games = play_games_async("BEST_SYM", "LATEST_SYM", len(claimed), conf['ENERGY'], 0, **kw)
+            finally:
+                pq.REFERENCE_Q21 = q21
         for game, gd in zip(claimed, games):
             winner_model = gd['winner_model']
             wins += winner_model == latest_model.name

@@ -7,6 +7,11 @@ import numpy as np
 from .symmetry import random_symmetry_predict
 
 _models = {}
+# Q21: in the reference the LATEST_SYM tag is evaluated by the BEST network (predicting_queue_worker.py:91-92) while its
+# *_NAME reports the latest model — NoModelEvaluateWorker therefore plays best against best and credits `latest`.
+# True reproduces that (the fixtures recorded from the reference need it); evaluate_worker.run_evaluation switches it
+# off for its own games unless told otherwise, so that the candidate network really is the one evaluated.
+REFERENCE_Q21 = True
 
 
 def register_models(best=None, latest=None):
@@ -17,7 +22,8 @@ def register_models(best=None, latest=None):
 
 
 def model_for(indicator):
-    base = 'BEST' if indicator in ('BEST', 'BEST_SYM', 'LATEST_SYM', 'BEST_NAME') else 'LATEST'
+    best_tags = ('BEST', 'BEST_SYM', 'BEST_NAME') + (('LATEST_SYM',) if REFERENCE_Q21 else ())
+    base = 'BEST' if indicator in best_tags else 'LATEST'
     if base not in _models:
         raise KeyError("no model registered for %s (call register_models)" % indicator)
     return _models[base]
