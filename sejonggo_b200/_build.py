@@ -25,20 +25,26 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+ABLATE_SO = os.path.join(LIBDIR, "libsejonggo_b200_ablate.so")
+
+
+def build(force=False, verbose=False, ablate=False):
+    """ablate=True builds a SECOND library with -DSGO_CONV_ABLATE (the conv kernel's timing-ablation switches read
+    from SGO_CONV_DEBUG; tools/conv_variants.py loads it through SGO_LIBRARY).  The product library has none."""
+    out = ABLATE_SO if ablate else SO
+    if not force and not ablate and not _stale():
         return SO
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.isfile(os.path.join(CSRC, s))]
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + srcs
+    cmd = [nvcc] + NVCC_FLAGS + (["-DSGO_CONV_ABLATE"] if ablate else []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout)
     if verbose:
         print(res.stdout)
-    return SO
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, ablate="--ablate" in sys.argv))

@@ -46,7 +46,8 @@ struct PairArgs {
     int W, P, rows_per_pos, YB, n_tiles, w_row0, relu;
     int n_taps, kchunks, halo;                // 9 x 4, halo P+1 for the tower convs; 1 x 3, halo 0 for the stem GEMM over the im2col tensor
     int dbg;                                  // timing ablations, compiled in only with -DSGO_CONV_ABLATE (tools/conv_variants.py): 1 = no epilogue
-                                              // global traffic, 2 = no A loads, 4 = no B loads, 32 = no activation stores, 64 = no skip loads
+                                              // global traffic, 2 = no A loads, 4 = no B loads, 32 = no activation stores, 64 = no skip loads,
+                                              // 8 = only W*W/(P*(W+1)) of the tiles (the time an ideal kernel without pad pixels / pad rows would take)
     const float *bias;
     const __nv_bfloat16 *skip;
     __nv_bfloat16 *out;                       // nullptr: do not store the activations (last layer feeding only the heads)

@@ -549,6 +549,9 @@ static int launch_conv(sgo_engine *e, sgo_tower *t, int n, int layer, int in, in
     pa.dbg = 0;
 #endif
     pa.n_tiles = (pa.YB * t->P + 255) / 256;
+#ifdef SGO_CONV_ABLATE
+    if (pa.dbg & 8) pa.n_tiles = (int)((long long)pa.n_tiles * t->W * t->W / (t->P * (t->W + 1)));     // results are garbage: timing only
+#endif
     pa.relu = 1; pa.err = t->err;
     if (layer >= 0) {
         pa.n_taps = 9; pa.kchunks = TW_C / TW_KCH; pa.w_row0 = layer * 9 * TW_C; pa.halo = t->P + 1;

@@ -55,7 +55,8 @@ def test_peaked_evaluator_long_games_default_sizing_equals_oracle():
     S, G, sims, batch = 9, 6, 96, 8
     m = PeakedModel()
     bg = BatchedGames((m, m), G, size=S, mode='a', mcts_batch_size=batch, mcts_simulations=sims, stop_exploration=0,
-                      self_play=True, rngs=[gl.SeededRng(40 + g) for g in range(G)], use_symmetry=False, num_moves=2 * S * S)
+                      self_play=True, rngs=[gl.SeededRng(40 + g) for g in range(G)], use_symmetry=True, num_moves=2 * S * S)
+    # (the oracle's play_game draws one symmetry per simulate batch from the same rng: the engine has to draw them too)
     bg.start()
     plies, peak = 0, 0
     while bg.step_ply(record=True):
@@ -71,8 +72,6 @@ def test_peaked_evaluator_long_games_default_sizing_equals_oracle():
     games = bg.finish()
     assert len(games) == G
     for g, got in enumerate(games):
-        ref = gl.play_game(PeakedModel(), None, sims, 0, self_play=True, num_moves=2 * S * S, size=S, mcts_batch_size=batch,
-                           rng=gl.SeededRng(40 + g)) if False else None
         mm = PeakedModel()
         ref = gl.play_game(mm, mm, sims, 0, self_play=True, num_moves=2 * S * S, size=S, mcts_batch_size=batch, rng=gl.SeededRng(40 + g))
         assert [x['move'] for x in got['moves']] == [x['move'] for x in ref['moves']], g
@@ -165,7 +164,7 @@ def test_slot_refill_games_equal_single_games(mode):
         pq.register_models(best=model, latest=model)
         from sejonggo_b200.batched import BatchedGames
         bg = BatchedGames((model, model), G, size=S, mode=mode, mcts_batch_size=batch, energy=batch, mcts_simulations=sims,
-                          stop_exploration=3, self_play=True, use_symmetry=False, n_total=N, resign=(-0.55, -0.55), num_moves=12,
+                          stop_exploration=3, self_play=True, use_symmetry=(mode == 'a'), n_total=N, resign=(-0.55, -0.55), num_moves=12,
                           rng_for_game=lambda gid: gl.SeededRng(900 + gid),
                           on_game_start=lambda gid: started.append(gid), on_game_end=lambda gid, gd: ended.append(gid))
         games = bg.run()                                # the games resign at different plies, so slots free up at different times
