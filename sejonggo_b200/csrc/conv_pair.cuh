@@ -52,10 +52,15 @@ struct PairArgs {
     const __nv_bfloat16 *skip;
     __nv_bfloat16 *out;                       // nullptr: do not store the activations (last layer feeding only the heads)
     int32_t *err;
-    // fused 1x1 head convolutions (model.py:73,83) on the last layer: feat[(pos*W*W + pix)*4 + {p0,p1,v0,v1}]
+    // fused 1x1 head convolutions (model.py:73,83) on the last layer: the post-ReLU features go out as the two fp32
+    // A matrices of the dense-head GEMMs, featp / featv [pos][feat_ld], column = pix*2 + channel (HWC flatten, model.py:76,86)
     const float *head_w4;                     // [C][4] folded weights, nullptr = off
     const float *head_b4;                     // [4]
-    float *feat;
+    float *featp, *featv;
+    int feat_ld;
+    // MODE 1 (dense heads as a TF32 GEMM, rows = positions): fp32 output [row][ldo], columns [0, ncols) of this N tile, rows < n_valid
+    float *outf;
+    int ldo, ncols, n_valid;
 };
 
 struct PairSmemTail {
@@ -97,6 +102,16 @@ __device__ __forceinline__ void umma2_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, 
                  "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
                  ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
+// fp32 operands read as TF32 (10-bit mantissa), K = 8 per instruction = the same 32 bytes per k-step as bf16 K = 16
+__device__ __forceinline__ void umma2_tf32_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+                 "mov.b64 da, {%1, %3};\n\t"
+                 "mov.b64 db, {%2, %3};\n\t"
+                 "setp.ne.b32 p, %5, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %4, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ bool elect_one()
 {
     uint32_t pred;
@@ -119,7 +134,13 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar)
 }
 // M=256 (pair), N=256, bf16 x bf16 -> f32, both operands K-major
 #define PR_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24))
+// the same shape with TF32 operands (format code 2)
+#define PR_IDESC_TF32 ((1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24))
 
+// MODE 0: the tower convolutions / stem GEMM (bf16 operands, bf16 activations out).
+// MODE 1: the dense heads (model.py:77-92) as plain GEMMs on the same pipeline: rows = positions, A = the fp32 feature
+//         matrix, B = the transposed dense weights, TF32 tensor-core math, fp32 rows out (+bias, ReLU on the value half).
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TW_THREADS, 1)
 k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
 {
@@ -130,6 +151,7 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    constexpr int KEL = MODE == 0 ? TW_KCH : TW_KCH / 2;          // elements per 128-byte K chunk: 64 bf16 / 32 fp32
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&maps.act) : "memory");
@@ -169,7 +191,7 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
                     if (!ok) break;
                     if (leader) {
                         if (rank == 0) mbar_expect_tx(&tail->a_full[slab], no_a ? 0u : 2u * slab_bytes);  // bytes of BOTH CTAs
-                        if (!no_a) tma2_load_2d(smem + (size_t)slab * PR_SLAB_BYTES, &maps.act, kc * TW_KCH, q_lo, &tail->a_full[slab]);
+                        if (!no_a) tma2_load_2d(smem + (size_t)slab * PR_SLAB_BYTES, &maps.act, kc * KEL, q_lo, &tail->a_full[slab]);
                     }
                     if (++slab == PR_SLABS) { slab = 0; sphase ^= 1; }
                     for (int tap = 0; tap < a.n_taps; tap++) {
@@ -177,7 +199,7 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
                         if (!ok) break;
                         if (leader) {
                             if (rank == 0) mbar_expect_tx(&tail->b_full[stage], no_b ? 0u : 2u * PR_B_BYTES);
-                            if (!no_b) tma2_load_2d(smem_b + (size_t)stage * PR_B_BYTES, &maps.w, kc * TW_KCH,
+                            if (!no_b) tma2_load_2d(smem_b + (size_t)stage * PR_B_BYTES, &maps.w, kc * KEL,
                                                     a.w_row0 + tap * TW_C + (int)rank * 128, &tail->b_full[stage]);
                         }
                         if (++stage == PR_BSTAGES) { stage = 0; phase ^= 1; }
@@ -219,7 +241,8 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
                         if (leader) {
 #pragma unroll
                             for (int k = 0; k < TW_KCH / 16; k++) {
-                                umma2_bf16_lohi(d_tmem, alo + 2 * k, blo + 2 * k, desc_hi, PR_IDESC, accum);
+                                if constexpr (MODE == 0) umma2_bf16_lohi(d_tmem, alo + 2 * k, blo + 2 * k, desc_hi, PR_IDESC, accum);
+                                else umma2_tf32_lohi(d_tmem, alo + 2 * k, blo + 2 * k, desc_hi, PR_IDESC_TF32, accum);
                                 accum = 1;
                             }
                             umma2_commit_mc(&tail->b_empty[stage]);                     // frees the weight slot in both CTAs
@@ -239,6 +262,37 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
         const int r = (int)rank * 128 + qw * 32 + lane;
         bool ok = true;
         int it = 0;
+        if constexpr (MODE == 1) {
+            // ---- dense-head GEMM epilogue: thread = one position; fp32 row out (+bias, ReLU for the value hidden layer)
+            for (int tile = pair; tile < a.n_tiles; tile += n_pairs, it++) {
+                const int acc = it & 1;
+                const int q = tile * 256 + r;
+                const bool valid = q < a.n_valid;
+                if (ok) ok = mbar_wait(&tail->tmem_full[acc], (it >> 1) & 1, a.err);
+                ok = __all_sync(SGO_FULL, ok);
+                if (!ok) break;
+                tc_fence_after();
+                const uint32_t t_addr = tmem_base + ((uint32_t)(qw * 32) << 16) + acc * 256;
+                float *orow = a.outf + (size_t)q * a.ldo;
+#pragma unroll 1
+                for (int c = 0; c < TW_C / 32; c++) {
+                    uint32_t v[32];
+                    tmem_ld32(t_addr + c * 32, v);
+                    if (valid && c * 32 < a.ncols) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            float f = __uint_as_float(v[j]) + tail->bias[c * 32 + j];
+                            if (a.relu) f = fmaxf(f, 0.f);
+                            v[j] = __float_as_uint(f);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; j++) stg256(orow + c * 32 + j * 8, v + j * 8);     // (the buffer is padded to whole 32-column groups)
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive_leader(&tail->tmem_empty[acc]);
+            }
+        } else
         for (int tile = pair; tile < a.n_tiles; tile += n_pairs, it++) {
             const int acc = it & 1;
             const int q = tile * 256 + r;
@@ -308,10 +362,9 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
             mbar_arrive_leader(&tail->tmem_empty[acc]);
             if (valid && a.head_w4) {
                 int pos = (yb - 1) / a.rows_per_pos, y = (yb - 1) - pos * a.rows_per_pos;
-                float4 r4;
-                r4.x = fmaxf(h0 + a.head_b4[0], 0.f); r4.y = fmaxf(h1 + a.head_b4[1], 0.f);
-                r4.z = fmaxf(h2 + a.head_b4[2], 0.f); r4.w = fmaxf(h3 + a.head_b4[3], 0.f);
-                reinterpret_cast<float4 *>(a.feat)[((size_t)pos * a.W + y) * a.W + x] = r4;
+                const size_t fo = (size_t)pos * a.feat_ld + (size_t)(y * a.W + x) * 2;
+                *reinterpret_cast<float2 *>(a.featp + fo) = make_float2(fmaxf(h0 + a.head_b4[0], 0.f), fmaxf(h1 + a.head_b4[1], 0.f));
+                *reinterpret_cast<float2 *>(a.featv + fo) = make_float2(fmaxf(h2 + a.head_b4[2], 0.f), fmaxf(h3 + a.head_b4[3], 0.f));
             }
         }
     }

@@ -8,8 +8,9 @@
 //          CTA pairs — TMA boxes per filter tap, tcgen05.mma.cta_group::2, double-buffered TMEM
 //          accumulators (conv_pair.cuh).
 //   heads  the two 1x1 convs are fused into the last conv's epilogue (its activations never
-//          reach HBM); k_heads_fc does the dense policy (softmax) / value (tanh) layers
-//          (model.py:72-92) in fp32 with the "reverse" symmetry policy gather fused in.
+//          reach HBM) and leave the two fp32 feature matrices; the dense layers Dense(578->362) and
+//          Dense(578->256) (model.py:80,90) are TF32 GEMMs on the same CTA-pair pipeline (conv_pair.cuh
+//          MODE 1); k_heads_finish does softmax, the "reverse" symmetry policy gather, Dense(256->1) and tanh.
 //
 // Activation layout in HBM: bf16 [YB][P][C], W = S-2 (Q11), P = W+1, YB = n_pos*(W+1)+1: every position owns W pixel
 // rows preceded by ONE all-zero pad row and every row ends in ONE all-zero pad pixel, so the halo of any pixel is
@@ -39,10 +40,17 @@ struct sgo_tower {
     float *pol_conv_w, *pol_conv_b, *pol_fc_w, *pol_fc_b;
     float *val_conv_w, *val_conv_b, *val_fc1_w, *val_fc1_b, *val_fc2_w, *val_fc2_b;
     __nv_bfloat16 *act[3];                  // [YB*P][C]
-    struct PairMaps *pmaps;                 // [0..2] tensor maps of the CTA-pair kernel per activation buffer (conv_pair.cuh); [3] = stem im2col
+    struct PairMaps *pmaps;                 // [0..2] tensor maps of the CTA-pair kernel per activation buffer (conv_pair.cuh); [3] = stem im2col;
+                                            // [4], [5] = dense heads: policy / value feature matrix + the transposed dense weights (fp32)
     __nv_bfloat16 *stem_col;                // [YB*P][TW_STEM_K] im2col of the input planes (0/1, +-1)
     __nv_bfloat16 *stem_wb;                 // [C co][TW_STEM_K] bf16 stem weights, k = tap*17 + plane
-    float *head_w4, *head_b4, *feat;        // fused 1x1 head convs: [C][4], [4]; features [max_pos][W*W][4]
+    float *head_w4, *head_b4;               // fused 1x1 head convs: [C][4], [4]
+    float *featp, *featv;                   // their post-ReLU outputs = A matrices of the dense heads: fp32 [max_pos][feat_ld], col = pix*2 + ch
+    int feat_ld;                            // 2*W*W rounded up to 32 (TF32 K chunks of 128 bytes); the pad columns stay zero
+    int pol_tiles;                          // 256-column N tiles of the policy layer: ceil(A / 256)
+    float *head_wt;                         // [(pol_tiles + 1) * 256][feat_ld] transposed dense weights: policy outputs, then the 256 value hidden units
+    float *head_bias;                       // [(pol_tiles + 1) * 256]
+    float *hbuf;                            // [max_pos][(pol_tiles + 1) * 256] policy logits | value hidden (post ReLU)
     int32_t *err;
     int sm_count;
     // optional live profiling (bench.py roofline): 4 events per forward call
@@ -222,176 +230,91 @@ __global__ void k_stem_weights(const float *w, __nv_bfloat16 *wb)
 }
 
 // ------------------------------------------------------------------ heads
-// Dense heads on the fused 1x1-conv features (feat[pos][pix][p0,p1,v0,v1], fp32, post BN+ReLU):
-// policy Dense(2P -> A) + softmax, value Dense(2P -> 256) + ReLU + Dense(256 -> 1) + tanh
-// (model.py:77-92).  A CTA owns FC_PB positions per pass: features sit transposed in shared
-// memory ([feature][position]) so one LDS.128 feeds 4 FMAs.  The weights stream through a
-// double-buffered cp.async stage (FC_KT pixels = 4*FC_KT weight rows at a time), so no global
-// load sits on the FMA chain; a thread owns TWO outputs x FC_PB positions (32 accumulators):
-// warps 0-5 the policy outputs, warps 6-9 the value hidden units, both running over the same
-// pixel loop.  Per output the sum runs bias, then pixels ascending, channel 0 then 1.
-#define FC_PB 16
-#define FC_THREADS 320
-#define FC_KT 8
-#define FC_VOFF 192                                // first thread of the value half
+// What is left after the two dense GEMMs (hbuf[pos] = policy logits [0, A) | value hidden units, ReLU'd, at column
+// vcol): softmax over the A logits, the "reverse" symmetry gather of the policy (symmetry.py:90-114; it re-uses the
+// forward map, Q8), Dense(256 -> 1) + tanh (model.py:91-92).  One warp per position; ~2.5 KB read, 1.5 KB written.
+#define HF_WARPS 8
 
-struct FcArgs {
-    int n, S, W, scatter;
+struct FinishArgs {
+    int n, S, A, ld, vcol, scatter;
     const int32_t *index, *syms;
-    const float *feat;
-    const float *pfw, *pfb, *v1w, *v1b, *v2w, *v2b;
+    const float *hbuf, *v2w, *v2b;
     float *policy, *value;
 };
 
-__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+__global__ void __launch_bounds__(HF_WARPS * 32)
+k_heads_finish(FinishArgs h)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-static inline int fc_smem_bytes(int P, int A)
-{
-    return (int)sizeof(float) * (4 * P * FC_PB + 2 * FC_KT * (2 * A + 512) + FC_PB * (FC_THREADS / 32));
-}
-
-__global__ void __launch_bounds__(FC_THREADS, 1)
-k_heads_fc(FcArgs h)
-{
-    extern __shared__ float fs[];
-    const int W = h.W, P = W * W, A = h.S * h.S + 1;
-    const int tileF = 2 * A + 512;                   // floats per pixel in a stage: policy rows (ch 0, 1), then value rows (ch 0, 1)
-    float *sfeat = fs;                               // [4P][FC_PB]; re-used as logit [FC_PB][A] once the sums are done (16A <= 64P for S >= 5)
-    float *wt = sfeat + (size_t)4 * P * FC_PB;       // [2][FC_KT][tileF]
-    float *vpart = wt + 2 * FC_KT * tileF;           // [FC_PB][FC_THREADS/32]
-    float *logit = sfeat;
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const int n_stage = (P + FC_KT - 1) / FC_KT;
-    const bool is_val = t >= FC_VOFF, is_pol = !is_val && 2 * t < A;
-    const int o0 = is_val ? 2 * (t - FC_VOFF) : 2 * t;                 // this thread's outputs o0, o0+1
-    const int rowlen = is_val ? 256 : A;
-    const bool two = o0 + 1 < rowlen;
-
-    auto load_stage = [&](int s, int buf) {
-        for (int pi = 0; pi < FC_KT; pi++) {
-            const int pix = s * FC_KT + pi;
-            if (pix >= P) break;
-            float *dst = wt + (size_t)(buf * FC_KT + pi) * tileF;
-            const float *srcp = h.pfw + (size_t)pix * 2 * A;           // rows (pix*2 + ch), flatten order HWC
-            if (!(A & 1)) { for (int c = t; c < A / 2; c += FC_THREADS) cp_async16(dst + 4 * c, srcp + 4 * c); }   // 8A bytes: 16-B chunks when A is even
-            else { for (int c = t; c < A; c += FC_THREADS) cp_async8(dst + 2 * c, srcp + 2 * c); }
-            const float *srcv = h.v1w + (size_t)pix * 512;
-            if (!(A & 1)) { for (int c = t; c < 128; c += FC_THREADS) cp_async16(dst + 2 * A + 4 * c, srcv + 4 * c); }
-            else { for (int c = t; c < 256; c += FC_THREADS) cp_async8(dst + 2 * A + 2 * c, srcv + 2 * c); }
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * HF_WARPS + (threadIdx.x >> 5);
+    if (i >= h.n) return;
+    const float *row = h.hbuf + (size_t)i * h.ld;
+    float lg[SGO_AWORDS];
+    float mx = -3.4e38f;
+#pragma unroll
+    for (int it = 0; it < SGO_AWORDS; it++) {
+        const int a0 = it * 32 + lane;
+        lg[it] = a0 < h.A ? row[a0] : -3.4e38f;
+        mx = fmaxf(mx, lg[it]);
+    }
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(SGO_FULL, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int it = 0; it < SGO_AWORDS; it++) {
+        const int a0 = it * 32 + lane;
+        lg[it] = a0 < h.A ? expf(lg[it] - mx) : 0.f;
+        sum += lg[it];
+    }
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(SGO_FULL, sum, o);
+    const float inv = 1.f / sum;
+    const size_t orow = h.scatter ? (size_t)(h.index ? h.index[i] : i) : (size_t)i;
+    const int sym = h.syms ? (h.syms[i] & 7) : 0;
+    float *pout = h.policy + orow * h.A;
+    if (sym == 0) {
+#pragma unroll
+        for (int it = 0; it < SGO_AWORDS; it++) {
+            const int a0 = it * 32 + lane;
+            if (a0 < h.A) pout[a0] = lg[it] * inv;
         }
-        cp_async_commit();
-    };
-
-    for (int base = blockIdx.x * FC_PB; base < h.n; base += gridDim.x * FC_PB) {
-        const int np = min(FC_PB, h.n - base);
-        __syncthreads();                                               // the previous pass is done with logit / vpart
-        load_stage(0, 0);
-        for (int i0 = t; i0 < 4 * P * FC_PB; i0 += 8 * FC_THREADS) {   // 8 independent global loads in flight per thread
-            float v[8];
+    } else {
+        // out[a] = softmax[g(a)]: the value sits in lane g(a) % 32, register g(a) / 32 -> go through shared memory
+        __shared__ float sp[HF_WARPS][SGO_APAD];
+        float *mine = sp[threadIdx.x >> 5];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int i = i0 + j * FC_THREADS, p = i / (4 * P);   // coalesced read of position p's features
-                v[j] = (i < 4 * P * FC_PB && p < np) ? h.feat[(size_t)base * 4 * P + i] : 0.f;
+        for (int it = 0; it < SGO_AWORDS; it++) mine[it * 32 + lane] = lg[it] * inv;
+        __syncwarp();
+        for (int a0 = lane; a0 < h.A; a0 += 32) {
+            int src = a0;
+            if (a0 < h.S * h.S) {
+                int y = a0 / h.S, x = a0 - y * h.S, sy, sx;
+                sym_src_t(h.S, sym, y, x, sy, sx);
+                src = sy * h.S + sx;
             }
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int i = i0 + j * FC_THREADS, p = i / (4 * P), f = i - p * 4 * P;
-                if (i < 4 * P * FC_PB) sfeat[f * FC_PB + p] = v[j];
-            }
-        }
-        float acc0[FC_PB], acc1[FC_PB];
-        {
-            const float *bias = is_val ? h.v1b : h.pfb;
-            const float b0 = (is_pol || is_val) ? bias[o0] : 0.f, b1 = ((is_pol || is_val) && two) ? bias[o0 + 1] : 0.f;
-#pragma unroll
-            for (int p = 0; p < FC_PB; p++) { acc0[p] = b0; acc1[p] = b1; }
-        }
-        for (int s = 0; s < n_stage; s++) {
-            if (s + 1 < n_stage) { load_stage(s + 1, (s + 1) & 1); cp_async_wait<1>(); }
-            else cp_async_wait<0>();
-            __syncthreads();                                           // stage s (and, at s = 0, the features) visible to all
-            if (is_pol || is_val) {
-                for (int pi = 0; pi < FC_KT; pi++) {
-                    const int pix = s * FC_KT + pi;
-                    if (pix >= P) break;
-                    const float *wrow = wt + (size_t)((s & 1) * FC_KT + pi) * tileF + (is_val ? 2 * A : 0);
-                    const float *frow = sfeat + (size_t)(pix * 4 + (is_val ? 2 : 0)) * FC_PB;
-#pragma unroll
-                    for (int ch = 0; ch < 2; ch++) {
-                        const float w0 = wrow[ch * rowlen + o0], w1 = two ? wrow[ch * rowlen + o0 + 1] : 0.f;
-                        const float4 *f4 = reinterpret_cast<const float4 *>(frow + ch * FC_PB);
-#pragma unroll
-                        for (int q = 0; q < FC_PB / 4; q++) {
-                            const float4 f = f4[q];
-                            acc0[4 * q] = fmaf(f.x, w0, acc0[4 * q]); acc0[4 * q + 1] = fmaf(f.y, w0, acc0[4 * q + 1]);
-                            acc0[4 * q + 2] = fmaf(f.z, w0, acc0[4 * q + 2]); acc0[4 * q + 3] = fmaf(f.w, w0, acc0[4 * q + 3]);
-                            acc1[4 * q] = fmaf(f.x, w1, acc1[4 * q]); acc1[4 * q + 1] = fmaf(f.y, w1, acc1[4 * q + 1]);
-                            acc1[4 * q + 2] = fmaf(f.z, w1, acc1[4 * q + 2]); acc1[4 * q + 3] = fmaf(f.w, w1, acc1[4 * q + 3]);
-                        }
-                    }
-                }
-            }
-            __syncthreads();                                           // buffer (s & 1) may be refilled; after the last stage: sfeat is free
-        }
-        if (is_pol) {
-#pragma unroll
-            for (int p = 0; p < FC_PB; p++) {
-                logit[p * A + o0] = acc0[p];
-                if (two) logit[p * A + o0 + 1] = acc1[p];
-            }
-        }
-        {                                                               // value: ReLU, Dense(256 -> 1) partial sums per warp
-            const float w2a = is_val ? h.v2w[o0] : 0.f, w2b = is_val ? h.v2w[o0 + 1] : 0.f;
-#pragma unroll
-            for (int p = 0; p < FC_PB; p++) {
-                float v = is_val ? fmaf(fmaxf(acc0[p], 0.f), w2a, fmaxf(acc1[p], 0.f) * w2b) : 0.f;
-                for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(SGO_FULL, v, o);
-                if (lane == 0) vpart[p * (FC_THREADS / 32) + warp] = v;
-            }
-        }
-        __syncthreads();
-        // softmax + outputs: one warp per position
-        for (int p = warp; p < np; p += FC_THREADS / 32) {
-            float mx = -3.4e38f;
-            for (int a0 = lane; a0 < A; a0 += 32) mx = fmaxf(mx, logit[p * A + a0]);
-            for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(SGO_FULL, mx, o));
-            float sum = 0.f;
-            for (int a0 = lane; a0 < A; a0 += 32) {
-                float ev = expf(logit[p * A + a0] - mx);
-                logit[p * A + a0] = ev;
-                sum += ev;
-            }
-            for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(SGO_FULL, sum, o);
-            __syncwarp();
-            const int i = base + p;
-            const size_t orow = h.scatter ? (size_t)(h.index ? h.index[i] : i) : (size_t)i;
-            const int sym = h.syms ? (h.syms[i] & 7) : 0;
-            const float inv = 1.f / sum;
-            for (int a0 = lane; a0 < A; a0 += 32) {
-                int src = a0;
-                if (a0 < h.S * h.S) {                               // "reverse" gather re-uses the forward map (Q8)
-                    int y = a0 / h.S, x = a0 - y * h.S, sy, sx;
-                    sym_src_t(h.S, sym, y, x, sy, sx);
-                    src = sy * h.S + sx;
-                }
-                h.policy[orow * A + a0] = logit[p * A + src] * inv;
-            }
-            if (lane == 0) {
-                float vs = h.v2b[0];
-                for (int w8 = FC_VOFF / 32; w8 < FC_THREADS / 32; w8++) vs += vpart[p * (FC_THREADS / 32) + w8];
-                h.value[orow] = tanhf(vs);
-            }
+            pout[a0] = mine[src];
         }
     }
+    float vs = 0.f;
+    for (int k = lane; k < 256; k += 32) vs = fmaf(row[h.vcol + k], h.v2w[k], vs);
+    for (int o = 16; o; o >>= 1) vs += __shfl_xor_sync(SGO_FULL, vs, o);
+    if (lane == 0) h.value[orow] = tanhf(vs + h.v2b[0]);
+}
+
+// dense weights [F][A] and [F][256] (Keras: y = x @ W) -> one transposed, padded fp32 matrix [(pol_tiles+1)*256][ld]
+// (row = output unit, K-major) + the padded bias vector
+__global__ void k_head_wt(const float *pfw, const float *pfb, const float *v1w, const float *v1b, int F, int A, int ld, int pol_tiles,
+                          float *wt, float *bias)
+{
+    const int rows = (pol_tiles + 1) * 256;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows * ld) return;
+    const int r = (int)(i / ld), k = (int)(i - (size_t)r * ld);
+    float v = 0.f;
+    if (k < F) {
+        if (r < pol_tiles * 256) { if (r < A) v = pfw[(size_t)k * A + r]; }
+        else v = v1w[(size_t)k * 256 + (r - pol_tiles * 256)];
+    }
+    wt[i] = v;
+    if (k == 0) bias[r] = r < pol_tiles * 256 ? (r < A ? pfb[r] : 0.f) : v1b[r - pol_tiles * 256];
 }
 
 // ------------------------------------------------------------------ host side
@@ -416,8 +339,8 @@ static int make_maps(sgo_engine *e, sgo_tower *t)
     PFN_encodeTiled enc = get_encode();
     if (!enc) return sgo_fail(e, "cuTensorMapEncodeTiled unavailable");
     cuuint32_t es[2] = {1, 1};
-    t->pmaps = new PairMaps[4];
-    memset(t->pmaps, 0, sizeof(PairMaps) * 4);
+    t->pmaps = new PairMaps[6];
+    memset(t->pmaps, 0, sizeof(PairMaps) * 6);
     const cuuint64_t Q = (cuuint64_t)t->YB * t->P;
     for (int i = 0; i < 4; i++) {                          // activation buffers [0..2], stem im2col [3]
         const int kw = i < 3 ? TW_C : TW_STEM_K, halo = i < 3 ? t->P + 1 : 0;
@@ -435,6 +358,20 @@ static int make_maps(sgo_engine *e, sgo_tower *t)
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (rr != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(weights) failed");
     }
+    for (int i = 4; i < 6; i++) {                          // dense heads: fp32, 32 elements = 128 bytes per K chunk
+        cuuint64_t dims[2] = {(cuuint64_t)t->feat_ld, (cuuint64_t)t->max_pos};
+        cuuint64_t strides[1] = {(cuuint64_t)t->feat_ld * 4};
+        cuuint32_t box[2] = {TW_KCH / 2, 128};
+        CUresult rr = enc(&t->pmaps[i].act, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, i == 4 ? (void *)t->featp : (void *)t->featv, dims, strides,
+                          box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rr != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(head features) failed");
+        cuuint64_t wdims[2] = {(cuuint64_t)t->feat_ld, (cuuint64_t)(t->pol_tiles + 1) * 256};
+        rr = enc(&t->pmaps[i].w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)t->head_wt, wdims, strides, box, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rr != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(head weights) failed");
+    }
     return 0;
 }
 
@@ -447,7 +384,8 @@ static void tower_free(sgo_tower *t)
     cudaFree(t->val_fc2_w); cudaFree(t->val_fc2_b);
     for (int i = 0; i < 3; i++) cudaFree(t->act[i]);
     cudaFree(t->err);
-    cudaFree(t->stem_col); cudaFree(t->stem_wb); cudaFree(t->head_w4); cudaFree(t->head_b4); cudaFree(t->feat);
+    cudaFree(t->stem_col); cudaFree(t->stem_wb); cudaFree(t->head_w4); cudaFree(t->head_b4);
+    cudaFree(t->featp); cudaFree(t->featv); cudaFree(t->head_wt); cudaFree(t->head_bias); cudaFree(t->hbuf);
     delete[] t->pmaps;
     if (t->prof_ev) {
         for (int i = 0; i < TW_PROF_MAX * 4; i++) cudaEventDestroy(t->prof_ev[i]);
@@ -515,16 +453,32 @@ extern "C" int sgo_tower_load_weights(sgo_engine *e, int32_t slot, const sgo_tow
     SGO_CUDA_OK(e, cudaGetLastError());
     SGO_CUDA_OK(e, cudaMalloc(&t->head_w4, sizeof(float) * TW_C * 4));
     SGO_CUDA_OK(e, cudaMalloc(&t->head_b4, sizeof(float) * 4));
-    SGO_CUDA_OK(e, cudaMalloc(&t->feat, sizeof(float) * 4 * (size_t)P * max_positions));
     k_head_w4<<<1, TW_C, 0, S_(stream)>>>(t->pol_conv_w, t->pol_conv_b, t->val_conv_w, t->val_conv_b, t->head_w4, t->head_b4);
     SGO_CUDA_OK(e, cudaGetLastError());
-    SGO_CUDA_OK(e, cudaFuncSetAttribute(k_heads_fc, cudaFuncAttributeMaxDynamicSharedMemorySize, fc_smem_bytes(P, A)));
+    // dense heads as TF32 GEMMs: feature matrices (pad columns zero for ever), transposed weights, output rows
+    t->feat_ld = (2 * P + 31) / 32 * 32;
+    t->pol_tiles = (A + 255) / 256;
+    {
+        const size_t fb = sizeof(float) * (size_t)t->feat_ld * max_positions, rows = (size_t)(t->pol_tiles + 1) * 256;
+        SGO_CUDA_OK(e, cudaMalloc(&t->featp, fb));
+        SGO_CUDA_OK(e, cudaMalloc(&t->featv, fb));
+        SGO_CUDA_OK(e, cudaMemsetAsync(t->featp, 0, fb, S_(stream)));
+        SGO_CUDA_OK(e, cudaMemsetAsync(t->featv, 0, fb, S_(stream)));
+        SGO_CUDA_OK(e, cudaMalloc(&t->head_wt, sizeof(float) * rows * t->feat_ld));
+        SGO_CUDA_OK(e, cudaMalloc(&t->head_bias, sizeof(float) * rows));
+        SGO_CUDA_OK(e, cudaMalloc(&t->hbuf, sizeof(float) * rows * max_positions));
+        const size_t tot = rows * t->feat_ld;
+        k_head_wt<<<(unsigned)((tot + 255) / 256), 256, 0, S_(stream)>>>(t->pol_fc_w, t->pol_fc_b, t->val_fc1_w, t->val_fc1_b, 2 * P, A,
+                                                                        t->feat_ld, t->pol_tiles, t->head_wt, t->head_bias);
+        SGO_CUDA_OK(e, cudaGetLastError());
+    }
     SGO_CUDA_OK(e, cudaMalloc(&t->err, sizeof(int32_t)));
     SGO_CUDA_OK(e, cudaMemsetAsync(t->err, 0, sizeof(int32_t), S_(stream)));
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev);
-    SGO_CUDA_OK(e, cudaFuncSetAttribute(k_conv3x3_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM_BYTES));
+    SGO_CUDA_OK(e, cudaFuncSetAttribute(k_conv3x3_pair<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM_BYTES));
+    SGO_CUDA_OK(e, cudaFuncSetAttribute(k_conv3x3_pair<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM_BYTES));
     int rc = make_maps(e, t);
     if (rc) return rc;
     SGO_CUDA_OK(e, cudaStreamSynchronize(S_(stream)));
@@ -562,10 +516,42 @@ static int launch_conv(sgo_engine *e, sgo_tower *t, int n, int layer, int in, in
     }
     pa.skip = skip >= 0 ? t->act[skip] : nullptr;
     pa.out = heads ? nullptr : t->act[out];      // the last layer's activations are consumed by the fused 1x1 head convs only
-    pa.head_w4 = heads ? t->head_w4 : nullptr; pa.head_b4 = t->head_b4; pa.feat = t->feat;
+    pa.head_w4 = heads ? t->head_w4 : nullptr; pa.head_b4 = t->head_b4;
+    pa.featp = t->featp; pa.featv = t->featv; pa.feat_ld = t->feat_ld;
+    pa.outf = nullptr; pa.ldo = pa.ncols = pa.n_valid = 0;
     int pairs = t->sm_count / 2;
     if (pairs > pa.n_tiles) pairs = pa.n_tiles;
-    k_conv3x3_pair<<<2 * pairs, TW_THREADS, PR_SMEM_BYTES, S_(stream)>>>(t->pmaps[layer >= 0 ? in : 3], pa);
+    k_conv3x3_pair<0><<<2 * pairs, TW_THREADS, PR_SMEM_BYTES, S_(stream)>>>(t->pmaps[layer >= 0 ? in : 3], pa);
+    SGO_LAUNCHED(e);
+    return 0;
+}
+
+// the dense heads of n positions: (pol_tiles + 1) launches of the pair kernel in MODE 1 (one 256-column N tile each:
+// the policy outputs, then the value hidden layer), then k_heads_finish
+static int launch_heads(sgo_engine *e, sgo_tower *t, int n, const int32_t *d_index, const int32_t *d_sym, int scatter,
+                        float *d_policy, float *d_value, void *stream)
+{
+    const int ld = (t->pol_tiles + 1) * 256;
+    for (int nt = 0; nt <= t->pol_tiles; nt++) {
+        PairArgs pa;
+        memset(&pa, 0, sizeof(pa));
+        pa.W = t->W; pa.P = t->P; pa.rows_per_pos = t->W + 1; pa.YB = 0;
+        pa.n_tiles = (n + 255) / 256;
+        pa.n_taps = 1; pa.kchunks = t->feat_ld / 32; pa.halo = 0; pa.w_row0 = nt * 256;
+        pa.relu = nt == t->pol_tiles;                         // Dense(256, relu) of the value head; the policy logits go to the softmax raw
+        pa.bias = t->head_bias + nt * 256;
+        pa.err = t->err;
+        pa.outf = t->hbuf + nt * 256; pa.ldo = ld; pa.n_valid = n;
+        pa.ncols = nt < t->pol_tiles ? (e->A - nt * 256 < 256 ? e->A - nt * 256 : 256) : 256;
+        int pairs = t->sm_count / 2;
+        if (pairs > pa.n_tiles) pairs = pa.n_tiles;
+        k_conv3x3_pair<1><<<2 * pairs, TW_THREADS, PR_SMEM_BYTES, S_(stream)>>>(t->pmaps[nt < t->pol_tiles ? 4 : 5], pa);
+        SGO_LAUNCHED(e);
+    }
+    FinishArgs f;
+    f.n = n; f.S = t->S; f.A = e->A; f.ld = ld; f.vcol = t->pol_tiles * 256; f.scatter = scatter; f.index = d_index; f.syms = d_sym;
+    f.hbuf = t->hbuf; f.v2w = t->val_fc2_w; f.v2b = t->val_fc2_b; f.policy = d_policy; f.value = d_value;
+    k_heads_finish<<<(n + HF_WARPS - 1) / HF_WARPS, HF_WARPS * 32, 0, S_(stream)>>>(f);
     SGO_LAUNCHED(e);
     return 0;
 }
@@ -605,15 +591,10 @@ extern "C" int sgo_tower_forward(sgo_engine *e, int32_t slot, int32_t which, con
         x = y;
     }
     if (prof) cudaEventRecord(pe[2], S_(stream));
-    FcArgs f;
-    f.n = n; f.S = t->S; f.W = t->W; f.scatter = scatter; f.index = d_index; f.syms = d_sym; f.feat = t->feat;
-    f.pfw = t->pol_fc_w; f.pfb = t->pol_fc_b; f.v1w = t->val_fc1_w; f.v1b = t->val_fc1_b; f.v2w = t->val_fc2_w; f.v2b = t->val_fc2_b;
-    f.policy = d_policy; f.value = d_value;
-    int fs = fc_smem_bytes(P, e->A);
-    int fgrid = (n + FC_PB - 1) / FC_PB;
-    if (fgrid > t->sm_count) fgrid = t->sm_count;
-    k_heads_fc<<<fgrid, FC_THREADS, fs, S_(stream)>>>(f);
-    SGO_LAUNCHED(e);
+    {
+        int rc = launch_heads(e, t, n, d_index, d_sym, scatter, d_policy, d_value, stream);
+        if (rc) return rc;
+    }
     if (prof) { cudaEventRecord(pe[3], S_(stream)); t->prof_pos[t->prof_n++] = n; }
     return 0;
 }

@@ -58,16 +58,16 @@ def test_peaked_evaluator_long_games_default_sizing_equals_oracle():
                       self_play=True, rngs=[gl.SeededRng(40 + g) for g in range(G)], use_symmetry=True, num_moves=2 * S * S)
     # (the oracle's play_game draws one symmetry per simulate batch from the same rng: the engine has to draw them too)
     bg.start()
-    plies, peak = 0, 0
+    plies, sizes = 0, []
+    bg.after_search = lambda b, ts: sizes.append(int(b.eng.tree_sizes().max().item()))      # after the search, before the re-root
     while bg.step_ply(record=True):
         plies += 1
-        peak = max(peak, int(bg.eng.tree_sizes().max().item()))
         if plies % 20 == 0:
             st, owned = _pool_invariant(bg)
             assert st['failed_allocs'] == 0
     st, owned = _pool_invariant(bg)
     assert st['failed_allocs'] == 0 and bg.trees_dropped == 0 and plies >= 40
-    assert peak > 2 * sims                              # deep re-use: trees several plies' worth of nodes large
+    assert max(sizes) > 2 * sims                        # deep re-use: trees several plies' worth of nodes large
     bg.eng.check_errors()
     games = bg.finish()
     assert len(games) == G
@@ -107,10 +107,12 @@ def test_tree_outgrows_its_share_without_overflow():
     bg = BatchedGames((m, m), G, size=S, mode='a', mcts_batch_size=batch, mcts_simulations=sims, stop_exploration=0,
                       self_play=True, rng=gl.SeededRng(2), use_symmetry=False, arena_blocks=140, num_moves=30,
                       n_total=2)                     # only two of the eight slots ever play
+    sizes = []
+    bg.after_search = lambda b, ts: sizes.append(int(b.eng.tree_sizes().max().item()))      # after the search, before the re-root
     bg.start()
-    peak = 0
     while bg.step_ply(record=False):
-        peak = max(peak, int(bg.eng.tree_sizes().max().item()))
+        pass
+    peak = max(sizes)
     st = bg.eng.pool_stats()
     assert st['failed_allocs'] == 0 and bg.trees_dropped == 0
     assert peak > 140, peak                          # more than the average share: a fixed per-tree arena of that size would have overflowed
