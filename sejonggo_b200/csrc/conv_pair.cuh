@@ -6,15 +6,23 @@
 // A operand for each of the 9 filter taps cannot pass ~62% tensor-pipe utilisation (ncu: 61.6%).  So the A operand is
 // loaded ONCE per 64-channel chunk and the 9 taps are 9 MMAs on the same shared-memory slab with shifted descriptors:
 //
-//   activations in HBM:  bf16 [Q][C], Q = rows * P, P = W + 1: every image row carries one zero pad pixel (the right
-//   halo of row r is the left halo of row r+1) and every position one zero pad row, so filter tap (dy, dx) of output
-//   pixel q reads input pixel q + dy*P + dx for EVERY q — a uniform row shift of the GEMM's A operand.
-//   A pair tile = 256 consecutive q; per channel chunk each CTA loads its 128 rows plus a halo of P+1 rows on either
-//   side (ONE 2-D TMA box, 166 x 128 B) into a 128B-swizzled slab; tap (dy, dx) is the UMMA descriptor starting at
-//   slab + (halo + dy*P + dx) * 128 B.  SWIZZLE_128B is a function of the absolute smem address on both the TMA and the
-//   MMA side, so a descriptor may start at any 128-B row (tools/umma_rowshift_test.cu, verified on B200 with the
-//   descriptor's base-offset field left 0).  Operand traffic per tile drops from 2,304 KB to 1,322 KB; the pad pixels
-//   and pad rows cost 11% of the MACs (289 of 324 q per position are real pixels).
+//   activations in HBM:  bf16 [Q][C], DENSE: q = (position * W + y) * W + x, no padding of any kind.  Filter tap
+//   (dy, dx) of output pixel q reads input pixel q + dy*W + dx — a uniform row shift of the GEMM's A operand — which is
+//   the right neighbour except where it crosses an image edge (x + dx or y + dy outside 0..W-1: the shifted index lands
+//   in the neighbouring row / position).  Those (pixel, tap) products must contribute zero ("same" padding,
+//   model.py:39,42), and tcgen05.mma has exactly the operand for it: DISABLE-OUTPUT-LANE, a 256-bit mask of accumulator
+//   rows the instruction must not update.  Each tap's MMAs carry the mask of the rows whose neighbour is off the board;
+//   the centre tap is issued first (it is valid for every row, and the tile's first MMA overwrites the accumulator).
+//   The masks depend only on (first q of the tile) mod W*W: a table of W*W x 9 x 8 words built once per network
+//   (k_lane_masks); the issuing warp fetches the next tile's row while it issues the current tile.
+//   Round 1 padded instead (one zero pixel per row, one zero row per position: 324 q per 289 pixels), so 10.8% of the
+//   MMAs multiplied zeros; an ideal pad-free kernel was measured 12.8% faster (profiles/r02_conv_pad_bound.json).
+//   A pair tile = 256 consecutive q; per channel chunk each CTA loads its 128 rows plus a halo of W+1 rows on either
+//   side (ONE 2-D TMA box, 164 x 128 B, rows outside the tensor zero-filled) into a 128B-swizzled slab; tap (dy, dx) is
+//   the UMMA descriptor starting at slab + (halo + dy*W + dx) * 128 B.  SWIZZLE_128B is a function of the absolute smem
+//   address on both the TMA and the MMA side, so a descriptor may start at any 128-B row (tools/umma_rowshift_test.cu,
+//   verified on B200 with the descriptor's base-offset field left 0).  Operand traffic per tile: 1,322 KB instead of the
+//   2,304 KB of one A load per tap.
 //
 //   cluster (2,1,1); per CTA 192 threads: warp 0 TMA producer (both CTAs), warp 1 MMA issuer (leader CTA only) +
 //   TMEM alloc (both), warps 2-5 epilogue (both).  cta_group::2: each SM stages its own 128 A rows and half of the
@@ -32,7 +40,8 @@
 #define PR_DBG(bit) false                // the shipped library has no switch that makes the timed kernel skip work
 #endif
 #define PR_SLABS 3
-#define PR_SLAB_BYTES (21 * 1024)                  // >= (128 + 2 * (P + 1)) * 128 for P <= 18
+#define PR_SLAB_BYTES (21 * 1024)                  // >= (128 + 2 * (W + 1)) * 128 for W <= 19
+#define PR_MASK_WORDS 72                           // 9 taps (issue order) x 8 words of disable-output-lane mask per tile alignment
 #define PR_BSTAGES 8
 #define PR_B_BYTES (128 * 128)
 #define PR_MAX_HALO ((PR_SLAB_BYTES / 128 - 128) / 2)
@@ -43,11 +52,12 @@ struct PairMaps {
 };
 
 struct PairArgs {
-    int W, P, rows_per_pos, YB, n_tiles, w_row0, relu;
-    int n_taps, kchunks, halo;                // 9 x 4, halo P+1 for the tower convs; 1 x 3, halo 0 for the stem GEMM over the im2col tensor
+    int W, PX, Q, n_tiles, w_row0, relu;      // PX = W*W pixels per position, Q = positions * PX rows in all
+    int n_taps, kchunks, halo;                // 9 x 4, halo W+1 for the tower convs; 1 x 3, halo 0 for the stem GEMM over the im2col tensor
+    const uint32_t *masks;                    // [PX][PR_MASK_WORDS] lane masks by tile alignment (nullptr: one tap, nothing to mask)
     int dbg;                                  // timing ablations, compiled in only with -DSGO_CONV_ABLATE (tools/conv_variants.py): 1 = no epilogue
                                               // global traffic, 2 = no A loads, 4 = no B loads, 32 = no activation stores, 64 = no skip loads,
-                                              // 8 = only W*W/(P*(W+1)) of the tiles (the time an ideal kernel without pad pixels / pad rows would take)
+                                              // 16 = all lane masks zero (what the masks cost)
     const float *bias;
     const __nv_bfloat16 *skip;
     __nv_bfloat16 *out;                       // nullptr: do not store the activations (last layer feeding only the heads)
@@ -67,6 +77,7 @@ struct PairSmemTail {
     uint64_t a_full[PR_SLABS], a_empty[PR_SLABS], b_full[PR_BSTAGES], b_empty[PR_BSTAGES], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
     uint32_t pad;
+    alignas(16) uint32_t lane_masks[2][PR_MASK_WORDS + 8];       // this tile's / the next tile's masks (written and read by the MMA warp only)
     float bias[TW_C];
     float4 w4[TW_C];
 };
@@ -102,6 +113,19 @@ __device__ __forceinline__ void umma2_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, 
                  "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
                  ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
+// bf16 MMA that leaves the accumulator rows flagged in the 256-bit mask m0..m7 untouched (bit i of word w = row 32w + i of
+// the pair tile: rows 0-127 live in the leader CTA's TMEM lanes, 128-255 in its peer's)
+__device__ __forceinline__ void umma2_bf16_masked(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate,
+                                                  const uint4 &ma, const uint4 &mb)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+                 "mov.b64 da, {%1, %3};\n\t"
+                 "mov.b64 db, {%2, %3};\n\t"
+                 "setp.ne.b32 p, %5, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, {%6, %7, %8, %9, %10, %11, %12, %13}, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate),
+                   "r"(ma.x), "r"(ma.y), "r"(ma.z), "r"(ma.w), "r"(mb.x), "r"(mb.y), "r"(mb.z), "r"(mb.w) : "memory");
+}
 // fp32 operands read as TF32 (10-bit mantissa), K = 8 per instruction = the same 32 bytes per k-step as bf16 K = 16
 __device__ __forceinline__ void umma2_tf32_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate)
 {
@@ -132,6 +156,9 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar)
                  "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
                  ::"r"(smem_u32(bar)) : "memory");
 }
+// issue order of the 9 filter taps: the centre tap first (valid for every pixel: the first MMA of a tile overwrites the
+// accumulator, so it must not skip any row), then the rest in raster order.  tap = (dy + 1) * 3 + (dx + 1).
+__device__ __forceinline__ int tap_of(int i) { return i == 0 ? 4 : (i <= 4 ? i - 1 : i); }
 // M=256 (pair), N=256, bf16 x bf16 -> f32, both operands K-major
 #define PR_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24))
 // the same shape with TF32 operands (format code 2)
@@ -200,7 +227,7 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
                         if (leader) {
                             if (rank == 0) mbar_expect_tx(&tail->b_full[stage], no_b ? 0u : 2u * PR_B_BYTES);
                             if (!no_b) tma2_load_2d(smem_b + (size_t)stage * PR_B_BYTES, &maps.w, kc * KEL,
-                                                    a.w_row0 + tap * TW_C + (int)rank * 128, &tail->b_full[stage]);
+                                                    a.w_row0 + (a.n_taps == 1 ? 0 : tap_of(tap)) * TW_C + (int)rank * 128, &tail->b_full[stage]);
                         }
                         if (++stage == PR_BSTAGES) { stage = 0; phase ^= 1; }
                     }
@@ -209,7 +236,8 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
         }
     } else if (warp == 1) {
         if (rank == 0) {
-            // ---- MMA issuer: 9 taps x 4 K-steps on one slab, descriptor start shifted by (dy*P + dx) rows ------------
+            // ---- MMA issuer: 9 taps x 4 K-steps on one slab, descriptor start shifted by (dy*W + dx) rows, rows whose
+            // neighbour is off the board masked out of the update ---------------------------------------------------------
             // The WHOLE warp runs the (warp-uniform) control flow and the barrier waits; one elected lane issues.  Written
             // this way — and with the descriptors kept as a constant high word plus a running 32-bit low word — the loop
             // is ~45 SASS instructions per k-block instead of ~130 (a lane==0 branch makes nvcc wrap every tcgen05
@@ -220,10 +248,25 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
             const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);       // SBO 1024 B, version 1, SWIZZLE_128B
             const uint32_t a_lo0 = ((smem_u32(smem) & 0x3FFFF) >> 4) | (1u << 16);          // + slab * (PR_SLAB_BYTES >> 4)
             const uint32_t b_lo0 = ((smem_u32(smem_b) & 0x3FFFF) >> 4) | (1u << 16);        // + stage * (PR_B_BYTES >> 4)
+            // lane masks: lanes 0-17 move one 16-byte piece each of a tile's 288-byte table row; the row of the NEXT tile
+            // is requested at the start of a tile and parked in shared memory once the first channel chunk has been issued
+            const bool masked = MODE == 0 && a.masks != nullptr && !PR_DBG(16);
+            auto mask_row = [&](int tile) {
+                const int al = (int)(((long long)tile * 256) % a.PX);
+                return reinterpret_cast<const uint4 *>(a.masks + (size_t)al * PR_MASK_WORDS)[lane];
+            };
+            for (int i = lane; i < 2 * (PR_MASK_WORDS + 8); i += 32) (&tail->lane_masks[0][0])[i] = 0u;
+            __syncwarp();
+            if (masked && pair < a.n_tiles && lane < PR_MASK_WORDS / 4) reinterpret_cast<uint4 *>(tail->lane_masks[0])[lane] = mask_row(pair);
+            __syncwarp();
             bool ok = true;
             int it = 0;
             for (int tile = pair; tile < a.n_tiles && ok; tile += n_pairs, it++) {
                 const uint32_t d_tmem = tmem_base + (uint32_t)(it & 1) * 256u;
+                const bool fetch = masked && tile + n_pairs < a.n_tiles && lane < PR_MASK_WORDS / 4;
+                uint4 next_masks = make_uint4(0u, 0u, 0u, 0u);
+                if (fetch) next_masks = mask_row(tile + n_pairs);
+                const uint4 *mk = reinterpret_cast<const uint4 *>(tail->lane_masks[it & 1]);
                 ok = mbar_wait(&tail->tmem_empty[it & 1], ((it >> 1) & 1) ^ 1, a.err);  // both epilogues drained this stage
                 if (!ok) break;
                 tc_fence_after();
@@ -233,15 +276,17 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
                     if (!ok) break;
                     const uint32_t a_lo = a_lo0 + slab * (PR_SLAB_BYTES >> 4) + (uint32_t)a.halo * 8u;
                     for (int tap = 0; tap < a.n_taps; tap++) {
+                        const uint4 ma = mk[2 * tap], mb = mk[2 * tap + 1];             // (zeros when nothing is masked)
                         ok = mbar_wait(&tail->b_full[stage], phase, a.err);
                         if (!ok) break;
                         tc_fence_after();
-                        const int shift = a.n_taps == 1 ? 0 : (tap / 3 - 1) * a.P + (tap % 3 - 1);
+                        const int tp = tap_of(tap);
+                        const int shift = a.n_taps == 1 ? 0 : (tp / 3 - 1) * a.W + (tp % 3 - 1);
                         const uint32_t alo = a_lo + (uint32_t)(shift * 8), blo = b_lo0 + stage * (PR_B_BYTES >> 4);
                         if (leader) {
 #pragma unroll
                             for (int k = 0; k < TW_KCH / 16; k++) {
-                                if constexpr (MODE == 0) umma2_bf16_lohi(d_tmem, alo + 2 * k, blo + 2 * k, desc_hi, PR_IDESC, accum);
+                                if constexpr (MODE == 0) umma2_bf16_masked(d_tmem, alo + 2 * k, blo + 2 * k, desc_hi, PR_IDESC, accum, ma, mb);
                                 else umma2_tf32_lohi(d_tmem, alo + 2 * k, blo + 2 * k, desc_hi, PR_IDESC_TF32, accum);
                                 accum = 1;
                             }
@@ -252,12 +297,16 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
                     }
                     if (ok && leader) umma2_commit_mc(&tail->a_empty[slab]);            // frees the slab in both CTAs
                     if (++slab == PR_SLABS) { slab = 0; sphase ^= 1; }
+                    if (kc == 0) {                                                      // the next tile's masks have arrived by now
+                        if (fetch) reinterpret_cast<uint4 *>(tail->lane_masks[(it + 1) & 1])[lane] = next_masks;
+                        __syncwarp();
+                    }
                 }
                 if (ok && leader) umma2_commit_mc(&tail->tmem_full[it & 1]);
             }
         }
     } else {
-        // ---- epilogue: thread = one q (pixel incl. pads) of the pair tile ----------------------------------------------
+        // ---- epilogue: thread = one q (pixel) of the pair tile -------------------------------------------------------------
         const int qw = warp & 3;
         const int r = (int)rank * 128 + qw * 32 + lane;
         bool ok = true;
@@ -296,8 +345,7 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
         for (int tile = pair; tile < a.n_tiles; tile += n_pairs, it++) {
             const int acc = it & 1;
             const int q = tile * 256 + r;
-            const int yb = q / a.P, x = q - yb * a.P;
-            bool valid = x < a.W && yb < a.YB && (yb % a.rows_per_pos) != 0;         // pad pixels / pad rows stay zero
+            bool valid = q < a.Q;                                    // (only the last tile has rows past the end)
             if (PR_DBG(1)) valid = false;
             const size_t gofs = (size_t)q * TW_C;
             if (valid && a.skip) {                                   // idle until the MMAs finish: pull the skip row towards L2
@@ -361,8 +409,8 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
             tc_fence_before();
             mbar_arrive_leader(&tail->tmem_empty[acc]);
             if (valid && a.head_w4) {
-                int pos = (yb - 1) / a.rows_per_pos, y = (yb - 1) - pos * a.rows_per_pos;
-                const size_t fo = (size_t)pos * a.feat_ld + (size_t)(y * a.W + x) * 2;
+                const int pos = q / a.PX, pix = q - pos * a.PX;
+                const size_t fo = (size_t)pos * a.feat_ld + (size_t)pix * 2;
                 *reinterpret_cast<float2 *>(a.featp + fo) = make_float2(fmaxf(h0 + a.head_b4[0], 0.f), fmaxf(h1 + a.head_b4[1], 0.f));
                 *reinterpret_cast<float2 *>(a.featv + fo) = make_float2(fmaxf(h2 + a.head_b4[2], 0.f), fmaxf(h3 + a.head_b4[3], 0.f));
             }

@@ -12,12 +12,12 @@
 //          Dense(578->256) (model.py:80,90) are TF32 GEMMs on the same CTA-pair pipeline (conv_pair.cuh
 //          MODE 1); k_heads_finish does softmax, the "reverse" symmetry policy gather, Dense(256->1) and tanh.
 //
-// Activation layout in HBM: bf16 [YB][P][C], W = S-2 (Q11), P = W+1, YB = n_pos*(W+1)+1: every position owns W pixel
-// rows preceded by ONE all-zero pad row and every row ends in ONE all-zero pad pixel, so the halo of any pixel is
-// at a fixed offset (q + dy*P + dx) in the flattened pixel index q = row*P + x and the conv is a shifted GEMM
-// (conv_pair.cuh).  History of the layout (profiles/): row tiles with per-tap TMA boxes (r01_tower_bench_pair*.json),
-// real-row tiles (r01_conv_real_row_tiling_ab.json) and a dense 4-D layout (r01_experiment_dense_*.json) all re-load
-// the A operand once per tap and are bound by L2->SM bytes.
+// Activation layout in HBM: bf16 [Q][C], dense, q = (position * W + y) * W + x with W = S-2 (Q11).  The conv is a shifted
+// GEMM over q with the image edges handled by tcgen05's disable-output-lane masks (conv_pair.cuh).  History of the
+// layout (profiles/): row tiles with per-tap TMA boxes (r01_tower_bench_pair*.json), real-row tiles
+// (r01_conv_real_row_tiling_ab.json) and a dense 4-D layout (r01_experiment_dense_*.json) all re-loaded the A operand
+// once per tap and were bound by L2->SM bytes; round 1 ended on the shifted GEMM over a zero-PADDED q (18 x 18 slots per
+// 17 x 17 image: 10.8% of the MMAs on zeros, r02_conv_pad_bound.json); the lane masks remove the padding.
 #include "engine.h"
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -32,17 +32,18 @@
 #define TW_STEM_K 192                      // 9 taps x 17 planes = 153, padded to 3 x 64
 
 struct sgo_tower {
-    int n_blocks, S, W, P, max_pos, YB;      // P = W + 1 pixel pitch (one zero pad pixel per row); YB = padded rows
+    int n_blocks, S, W, PX, max_pos;         // PX = W*W pixels per position
     int n_layers;
     float *stem_w, *stem_b;                 // [9][17][C], [C]
     __nv_bfloat16 *conv_w;                  // [n_layers][9][C co][C ci]
     float *conv_b;                          // [n_layers][C]
     float *pol_conv_w, *pol_conv_b, *pol_fc_w, *pol_fc_b;
     float *val_conv_w, *val_conv_b, *val_fc1_w, *val_fc1_b, *val_fc2_w, *val_fc2_b;
-    __nv_bfloat16 *act[3];                  // [YB*P][C]
+    __nv_bfloat16 *act[3];                  // [max_pos*PX][C]
+    uint32_t *lane_masks;                   // [PX][PR_MASK_WORDS] disable-output-lane masks per tile alignment (conv_pair.cuh)
     struct PairMaps *pmaps;                 // [0..2] tensor maps of the CTA-pair kernel per activation buffer (conv_pair.cuh); [3] = stem im2col;
                                             // [4], [5] = dense heads: policy / value feature matrix + the transposed dense weights (fp32)
-    __nv_bfloat16 *stem_col;                // [YB*P][TW_STEM_K] im2col of the input planes (0/1, +-1)
+    __nv_bfloat16 *stem_col;                // [max_pos*PX][TW_STEM_K] im2col of the input planes (0/1, +-1)
     __nv_bfloat16 *stem_wb;                 // [C co][TW_STEM_K] bf16 stem weights, k = tap*17 + plane
     float *head_w4, *head_b4;               // fused 1x1 head convs: [C][4], [4]
     float *featp, *featv;                   // their post-ReLU outputs = A matrices of the dense heads: fp32 [max_pos][feat_ld], col = pix*2 + ch
@@ -161,7 +162,7 @@ __device__ __forceinline__ void im2col_sector(const uint32_t (&m)[9], uint32_t t
 }
 
 __global__ void __launch_bounds__(IM_THREADS)
-k_stem_im2col(const Board *boards, const int32_t *index, const int32_t *syms, int n, int S, __nv_bfloat16 *col /* [rows*(W+1)][TW_STEM_K] */)
+k_stem_im2col(const Board *boards, const int32_t *index, const int32_t *syms, int n, int S, __nv_bfloat16 *col /* [n*W*W][TW_STEM_K] */)
 {
     __shared__ uint16_t cell[IM_NP][SGO_MAXS * SGO_MAXS];
     __shared__ int s_tm[IM_NP];
@@ -200,13 +201,32 @@ k_stem_im2col(const Board *boards, const int32_t *index, const int32_t *syms, in
 #pragma unroll
             for (int tap = 0; tap < 9; tap++) m[tap] = cell[q][(y + tap / 3) * S + x + tap % 3];
             const uint32_t tmv = s_tm[q] == 1 ? 0x3F80u : 0xBF80u;           // bf16 +1 / -1 (plane 16)
-            __nv_bfloat16 *dst = col + (((size_t)(i0 + q) * (W + 1) + 1 + y) * (W + 1) + x) * TW_STEM_K;
+            __nv_bfloat16 *dst = col + ((size_t)(i0 + q) * PX + px) * TW_STEM_K;
             im2col_sector<0>(m, tmv, dst); im2col_sector<1>(m, tmv, dst); im2col_sector<2>(m, tmv, dst);
             im2col_sector<3>(m, tmv, dst); im2col_sector<4>(m, tmv, dst); im2col_sector<5>(m, tmv, dst);
             im2col_sector<6>(m, tmv, dst); im2col_sector<7>(m, tmv, dst); im2col_sector<8>(m, tmv, dst);
             im2col_sector<9>(m, tmv, dst); im2col_sector<10>(m, tmv, dst); im2col_sector<11>(m, tmv, dst);
         }
     }
+}
+
+// disable-output-lane masks of the 3x3 "same" convolution over the dense q layout (conv_pair.cuh): for a pair tile whose first
+// row is pixel `al` of a position, bit i of word w of tap-slot t is set when row 32w + i must NOT receive tap tap_of(t),
+// i.e. when its (dy, dx) neighbour lies off the W x W board.  One thread per (alignment, tap slot, word).
+__global__ void k_lane_masks(int W, uint32_t *masks)
+{
+    const int PX = W * W;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= PX * PR_MASK_WORDS) return;
+    const int al = i / PR_MASK_WORDS, r = i - al * PR_MASK_WORDS, t = r >> 3, w = r & 7;
+    const int tp = t == 0 ? 4 : (t <= 4 ? t - 1 : t);        // tap_of(t)
+    const int dy = tp / 3 - 1, dx = tp % 3 - 1;
+    uint32_t m = 0;
+    for (int b = 0; b < 32; b++) {
+        const int pix = (al + 32 * w + b) % PX, y = pix / W, x = pix - y * W;
+        if (x + dx < 0 || x + dx >= W || y + dy < 0 || y + dy >= W) m |= 1u << b;
+    }
+    masks[i] = m;
 }
 
 // 1x1 head conv weights [C][2] + [C][2] -> interleaved [C][4] (p0,p1,v0,v1) and biases [4]
@@ -341,9 +361,9 @@ static int make_maps(sgo_engine *e, sgo_tower *t)
     cuuint32_t es[2] = {1, 1};
     t->pmaps = new PairMaps[6];
     memset(t->pmaps, 0, sizeof(PairMaps) * 6);
-    const cuuint64_t Q = (cuuint64_t)t->YB * t->P;
+    const cuuint64_t Q = (cuuint64_t)t->max_pos * t->PX;
     for (int i = 0; i < 4; i++) {                          // activation buffers [0..2], stem im2col [3]
-        const int kw = i < 3 ? TW_C : TW_STEM_K, halo = i < 3 ? t->P + 1 : 0;
+        const int kw = i < 3 ? TW_C : TW_STEM_K, halo = i < 3 ? t->W + 1 : 0;
         cuuint64_t dims[2] = {(cuuint64_t)kw, Q};
         cuuint64_t strides[1] = {(cuuint64_t)kw * 2};
         cuuint32_t box[2] = {TW_KCH, (cuuint32_t)(128 + 2 * halo)};      // one CTA's 128 rows + the (dy, dx) halo on both sides
@@ -383,7 +403,7 @@ static void tower_free(sgo_tower *t)
     cudaFree(t->val_conv_w); cudaFree(t->val_conv_b); cudaFree(t->val_fc1_w); cudaFree(t->val_fc1_b);
     cudaFree(t->val_fc2_w); cudaFree(t->val_fc2_b);
     for (int i = 0; i < 3; i++) cudaFree(t->act[i]);
-    cudaFree(t->err);
+    cudaFree(t->err); cudaFree(t->lane_masks);
     cudaFree(t->stem_col); cudaFree(t->stem_wb); cudaFree(t->head_w4); cudaFree(t->head_b4);
     cudaFree(t->featp); cudaFree(t->featv); cudaFree(t->head_wt); cudaFree(t->head_bias); cudaFree(t->hbuf);
     delete[] t->pmaps;
@@ -421,10 +441,9 @@ extern "C" int sgo_tower_load_weights(sgo_engine *e, int32_t slot, const sgo_tow
     memset(t, 0, sizeof(*t));
     e->tower[slot] = t;
     t->n_blocks = w->n_blocks; t->n_layers = 2 * w->n_blocks; t->S = e->S; t->W = e->S - 2;
-    t->P = t->W + 1;
-    if (t->P + 1 > PR_MAX_HALO) return sgo_fail(e, "board too wide for the conv slab");
+    t->PX = t->W * t->W;
+    if (t->W + 1 > PR_MAX_HALO) return sgo_fail(e, "board too wide for the conv slab");
     t->max_pos = max_positions;
-    t->YB = max_positions * (t->W + 1) + 1;
     int P = t->W * t->W, A = e->A;
     DUP(t->stem_w, w->stem_w, 9 * 17 * TW_C, float);
     DUP(t->stem_b, w->stem_b, TW_C, float);
@@ -440,12 +459,15 @@ extern "C" int sgo_tower_load_weights(sgo_engine *e, int32_t slot, const sgo_tow
     DUP(t->val_fc1_b, w->val_fc1_b, 256, float);
     DUP(t->val_fc2_w, w->val_fc2_w, 256, float);
     DUP(t->val_fc2_b, w->val_fc2_b, 1, float);
-    size_t act_bytes = (size_t)t->YB * t->P * TW_C * sizeof(__nv_bfloat16);
+    size_t act_bytes = (size_t)max_positions * t->PX * TW_C * sizeof(__nv_bfloat16);
     for (int i = 0; i < 3; i++) {
         SGO_CUDA_OK(e, cudaMalloc(&t->act[i], act_bytes));
-        SGO_CUDA_OK(e, cudaMemsetAsync(t->act[i], 0, act_bytes, S_(stream)));     // pad rows and pad pixels stay zero forever
+        SGO_CUDA_OK(e, cudaMemsetAsync(t->act[i], 0, act_bytes, S_(stream)));
     }
-    size_t col_bytes = (size_t)t->YB * t->P * TW_STEM_K * sizeof(__nv_bfloat16);
+    SGO_CUDA_OK(e, cudaMalloc(&t->lane_masks, sizeof(uint32_t) * (size_t)t->PX * PR_MASK_WORDS));
+    k_lane_masks<<<(t->PX * PR_MASK_WORDS + 255) / 256, 256, 0, S_(stream)>>>(t->W, t->lane_masks);
+    SGO_CUDA_OK(e, cudaGetLastError());
+    size_t col_bytes = (size_t)max_positions * t->PX * TW_STEM_K * sizeof(__nv_bfloat16);
     SGO_CUDA_OK(e, cudaMalloc(&t->stem_col, col_bytes));
     SGO_CUDA_OK(e, cudaMemsetAsync(t->stem_col, 0, col_bytes, S_(stream)));
     SGO_CUDA_OK(e, cudaMalloc(&t->stem_wb, sizeof(__nv_bfloat16) * TW_C * TW_STEM_K));
@@ -495,24 +517,20 @@ extern "C" int sgo_tower_max_positions(sgo_engine *e, int32_t slot)
 static int launch_conv(sgo_engine *e, sgo_tower *t, int n, int layer, int in, int out, int skip, void *stream, bool heads = false)
 {
     PairArgs pa;
-    pa.W = t->W; pa.P = t->P; pa.rows_per_pos = t->W + 1;
-    pa.YB = n * (t->W + 1) + 1;
+    pa.W = t->W; pa.PX = t->PX; pa.Q = n * t->PX;
 #ifdef SGO_CONV_ABLATE
     { const char *d = getenv("SGO_CONV_DEBUG"); pa.dbg = d ? atoi(d) : 0; }
 #else
     pa.dbg = 0;
 #endif
-    pa.n_tiles = (pa.YB * t->P + 255) / 256;
-#ifdef SGO_CONV_ABLATE
-    if (pa.dbg & 8) pa.n_tiles = (int)((long long)pa.n_tiles * t->W * t->W / (t->P * (t->W + 1)));     // results are garbage: timing only
-#endif
+    pa.n_tiles = (pa.Q + 255) / 256;
     pa.relu = 1; pa.err = t->err;
     if (layer >= 0) {
-        pa.n_taps = 9; pa.kchunks = TW_C / TW_KCH; pa.w_row0 = layer * 9 * TW_C; pa.halo = t->P + 1;
-        pa.bias = t->conv_b + (size_t)layer * TW_C;
+        pa.n_taps = 9; pa.kchunks = TW_C / TW_KCH; pa.w_row0 = layer * 9 * TW_C; pa.halo = t->W + 1;
+        pa.bias = t->conv_b + (size_t)layer * TW_C; pa.masks = t->lane_masks;
     } else {
         pa.n_taps = 1; pa.kchunks = TW_STEM_K / TW_KCH; pa.w_row0 = 0; pa.halo = 0;
-        pa.bias = t->stem_b;
+        pa.bias = t->stem_b; pa.masks = nullptr;
     }
     pa.skip = skip >= 0 ? t->act[skip] : nullptr;
     pa.out = heads ? nullptr : t->act[out];      // the last layer's activations are consumed by the fused 1x1 head convs only
@@ -535,7 +553,7 @@ static int launch_heads(sgo_engine *e, sgo_tower *t, int n, const int32_t *d_ind
     for (int nt = 0; nt <= t->pol_tiles; nt++) {
         PairArgs pa;
         memset(&pa, 0, sizeof(pa));
-        pa.W = t->W; pa.P = t->P; pa.rows_per_pos = t->W + 1; pa.YB = 0;
+        pa.W = t->W; pa.PX = t->PX; pa.Q = n;
         pa.n_tiles = (n + 255) / 256;
         pa.n_taps = 1; pa.kchunks = t->feat_ld / 32; pa.halo = 0; pa.w_row0 = nt * 256;
         pa.relu = nt == t->pol_tiles;                         // Dense(256, relu) of the value head; the policy logits go to the softmax raw
@@ -659,13 +677,13 @@ extern "C" int sgo_tower_debug_conv(sgo_engine *e, int32_t slot, int32_t n, int3
     return launch_conv(e, t, n, layer, in, out, skip, stream);
 }
 
-// raw activation buffer access (bf16 [n*(W+1)+1][W+1][C]) for tests
+// raw activation buffer access (bf16 [n*W*W][C], dense) for tests
 extern "C" int sgo_tower_act_copy(sgo_engine *e, int32_t slot, int32_t buf, int32_t n, void *d_data, int32_t to_tower, void *stream)
 {
     if (slot < 0 || slot > 1 || !e->tower[slot]) return sgo_fail(e, "tower slot has no weights");
     sgo_tower *t = e->tower[slot];
     if (buf < 0 || buf > 2 || n < 1 || n > t->max_pos) return sgo_fail(e, "act_copy arguments out of range");
-    size_t bytes = ((size_t)n * (t->W + 1) + 1) * t->P * TW_C * sizeof(__nv_bfloat16);
+    size_t bytes = (size_t)n * t->PX * TW_C * sizeof(__nv_bfloat16);
     if (to_tower) SGO_CUDA_OK(e, cudaMemcpyAsync(t->act[buf], d_data, bytes, cudaMemcpyDeviceToDevice, S_(stream)));
     else SGO_CUDA_OK(e, cudaMemcpyAsync(d_data, t->act[buf], bytes, cudaMemcpyDeviceToDevice, S_(stream)));
     return 0;

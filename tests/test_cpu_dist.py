@@ -92,16 +92,22 @@ WORKER = textwrap.dedent('''
 ''')
 
 
-def test_world2_gloo(tmp_path):
-    script = tmp_path / "w.py"
-    script.write_text(WORKER % dict(root=ROOT, out=str(tmp_path)))
+def _launch(script):
     import socket
     with socket.socket() as sk:                      # a free port: a fixed one can still be in TIME_WAIT from the last run
         sk.bind(("127.0.0.1", 0))
         port = str(sk.getsockname()[1])
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", port, str(script)],
-                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    return subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                           "--master-addr", "127.0.0.1", "--master-port", port, str(script)],
+                          env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+
+
+def test_world2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(WORKER % dict(root=ROOT, out=str(tmp_path)))
+    r = _launch(script)
+    if r.returncode != 0 and "Address already in use" in r.stdout:       # the probed port was taken in between: once more
+        r = _launch(script)
     assert r.returncode == 0, r.stdout[-3000:]
-    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout, r.stdout[-3000:]
