@@ -266,7 +266,7 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
                 const bool fetch = masked && tile + n_pairs < a.n_tiles && lane < PR_MASK_WORDS / 4;
                 uint4 next_masks = make_uint4(0u, 0u, 0u, 0u);
                 if (fetch) next_masks = mask_row(tile + n_pairs);
-                const uint4 *mk = reinterpret_cast<const uint4 *>(tail->lane_masks[it & 1]);
+                const uint32_t mk = smem_u32(tail->lane_masks[it & 1]);                 // shared-space address of this tile's masks
                 ok = mbar_wait(&tail->tmem_empty[it & 1], ((it >> 1) & 1) ^ 1, a.err);  // both epilogues drained this stage
                 if (!ok) break;
                 tc_fence_after();
@@ -275,13 +275,16 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
                     ok = mbar_wait(&tail->a_full[slab], sphase, a.err);
                     if (!ok) break;
                     const uint32_t a_lo = a_lo0 + slab * (PR_SLAB_BYTES >> 4) + (uint32_t)a.halo * 8u;
-                    for (int tap = 0; tap < a.n_taps; tap++) {
-                        const uint4 ma = mk[2 * tap], mb = mk[2 * tap + 1];             // (zeros when nothing is masked)
+                    // one tap = wait for its weight block, 4 MMAs (K = 4 x 16) with its lane mask, free the block.  The 9-tap
+                    // loop is unrolled so that the tap's row shift and mask offsets are immediates: the issuing thread has
+                    // ~500 tensor cycles per tap, and every instruction between two UTCHMMA groups counts against them
+                    auto issue_tap = [&](const int tap, const int shift) {
+                        uint4 ma, mb;                                                   // (zeros when nothing is masked)
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ma.x), "=r"(ma.y), "=r"(ma.z), "=r"(ma.w) : "r"(mk + 32u * tap));
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(mb.x), "=r"(mb.y), "=r"(mb.z), "=r"(mb.w) : "r"(mk + 32u * tap + 16u));
                         ok = mbar_wait(&tail->b_full[stage], phase, a.err);
-                        if (!ok) break;
+                        if (!ok) return;
                         tc_fence_after();
-                        const int tp = tap_of(tap);
-                        const int shift = a.n_taps == 1 ? 0 : (tp / 3 - 1) * a.W + (tp % 3 - 1);
                         const uint32_t alo = a_lo + (uint32_t)(shift * 8), blo = b_lo0 + stage * (PR_B_BYTES >> 4);
                         if (leader) {
 #pragma unroll
@@ -294,6 +297,15 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
                         }
                         accum = 1;
                         if (++stage == PR_BSTAGES) { stage = 0; phase ^= 1; }
+                    };
+                    if (MODE == 0 && a.n_taps == 9) {
+#pragma unroll
+                        for (int tap = 0; tap < 9; tap++) {
+                            const int tp = tap == 0 ? 4 : (tap <= 4 ? tap - 1 : tap);   // tap_of(tap), folded at compile time
+                            if (ok) issue_tap(tap, (tp / 3 - 1) * a.W + (tp % 3 - 1));
+                        }
+                    } else {
+                        issue_tap(0, 0);
                     }
                     if (ok && leader) umma2_commit_mc(&tail->a_empty[slab]);            // frees the slab in both CTAs
                     if (++slab == PR_SLABS) { slab = 0; sphase ^= 1; }
