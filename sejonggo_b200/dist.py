@@ -88,7 +88,7 @@ def gather_rows(rows, dst=0):
     dist.all_gather(counts, count)
     counts = [int(c.item()) for c in counts]
     if rank == dst:
-        out, reqs = [], []
+        out, ops = [], []
         for r in range(world):
             if r == dst:
                 out.append(rows)
@@ -96,12 +96,13 @@ def gather_rows(rows, dst=0):
             buf = torch.empty((counts[r], RW), dtype=torch.int32, device=rows.device)
             out.append(buf)
             if counts[r]:
-                reqs.append(dist.irecv(buf, src=r))
-        for q in reqs:
+                ops.append(dist.P2POp(dist.irecv, buf, r))
+        for q in (dist.batch_isend_irecv(ops) if ops else []):
             q.wait()
         return out
     if rows.shape[0]:
-        dist.isend(rows.contiguous(), dst=dst).wait()
+        for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, rows.contiguous(), dst)]):
+            q.wait()
     return None
 
 
