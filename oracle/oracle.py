@@ -17,9 +17,23 @@ EVAL_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER
 
 
 def build(force=False):
+    """Compiles go_oracle.c when the library is missing or older than the source — under a file lock, so that several
+    processes starting together (torchrun ranks, pytest-xdist workers) do not run `make` into the same file at once."""
+    import fcntl
     src = os.path.join(_HERE, "go_oracle.c")
-    if force or not os.path.isfile(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-s", "-C", _HERE, "-B" if force else "-s"], stdout=subprocess.DEVNULL)
+
+    def stale():
+        return force or not os.path.isfile(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src)
+
+    if stale():
+        os.makedirs(os.path.dirname(_SO), exist_ok=True)
+        with open(os.path.join(os.path.dirname(_SO), ".build.lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if stale():
+                    subprocess.check_call(["make", "-s", "-C", _HERE, "-B" if force else "-s"], stdout=subprocess.DEVNULL)
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return _SO
 
 

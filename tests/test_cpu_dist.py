@@ -109,5 +109,8 @@ def test_world2_gloo(tmp_path):
     r = _launch(script)
     if r.returncode != 0 and "Address already in use" in r.stdout:       # the probed port was taken in between: once more
         r = _launch(script)
+    if r.returncode != 0 or "rank 0 ok" not in r.stdout:
+        with open("/tmp/sgo_dist_fail.log", "w") as f:
+            f.write(r.stdout)
     assert r.returncode == 0, r.stdout[-3000:]
     assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout, r.stdout[-3000:]
