@@ -464,8 +464,11 @@ def run_ours(a):
 
 
 def run_full_games(a, arm, rank, world):
-    """Whole games with slot refill: `--total` games through `--games` slots, games cut at `--num-moves` plies and
-    resigning at `--resign` (so that they end at different plies and slots free up one by one)."""
+    """Whole games with slot refill: `--total` games through `--games` slots.  A random-init network never resigns and
+    rarely passes, so every game would run to the same cap and all slots would turn over in the same ply; to load the
+    refill path the way real games do, each game gets its own length cap, uniform in [num_moves/3, num_moves]
+    (seeded), so slots free up ply by ply."""
+    import numpy as np
     import torch
     bg = arm.bg
     bg.n_total = a.total or 2 * a.games
@@ -473,6 +476,8 @@ def run_full_games(a, arm, rank, world):
     if a.resign is not None:
         bg.resign[0][:] = a.resign
         bg.resign[1][:] = a.resign
+    lens = np.random.RandomState(99 + rank).randint(max(1, bg.num_moves // 3), bg.num_moves + 1, size=bg.n_total)
+    bg.on_game_start = lambda gid: dict(num_moves=int(lens[gid]))
     ended = []
     bg.on_game_end = lambda gid, gd: ended.append(len(gd['moves']))
     bg.start()
@@ -486,13 +491,30 @@ def run_full_games(a, arm, rank, world):
     arm.sync_all()
     ms = ev0.elapsed_time(ev1)
     bg.finish()
+    whole_sims, total, lengths = bg.sim_count, bg.n_total, list(ended)
     st = bg.eng.pool_stats()
     steady = a.games * bg.sims * plies                      # what the same number of plies would do with every slot busy
-    out = dict(metric="selfplay_whole_games", value=bg.sim_count / (ms * 1e-3), unit="simulations/s", n_gpus=world,
-               games=len(ended), games_per_hour=len(ended) / (ms * 1e-3) * 3600, plies_stepped=plies, ms_total=ms,
-               slot_occupancy=bg.sim_count / max(1, steady), mean_game_plies=sum(ended) / max(1, len(ended)),
-               min_game_plies=min(ended) if ended else 0, max_game_plies=max(ended) if ended else 0,
-               config=dict(workload=arm.workload(), total_games=bg.n_total, slots=a.games, num_moves=bg.num_moves, resign=a.resign),
+    arm.sync_all()
+    # the steady-state figure on the same box, same process: a few more plies of a full batch
+    bg.n_total, bg.on_game_start = a.games, None
+    bg.start()
+    for _ in range(2):
+        bg.step_ply(record=True)
+    s0 = bg.sim_count
+    arm.sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        bg.step_ply(record=True)
+    e1.record()
+    arm.sync_all()
+    steady_rate = (bg.sim_count - s0) / (e0.elapsed_time(e1) * 1e-3)
+    out = dict(metric="selfplay_whole_games", value=whole_sims / (ms * 1e-3), unit="simulations/s", n_gpus=world,
+               games=len(lengths), games_per_hour=len(lengths) / (ms * 1e-3) * 3600, plies_stepped=plies, ms_total=ms,
+               slot_occupancy=whole_sims / max(1, steady), steady_state_sims_per_s=steady_rate,
+               whole_run_over_steady_state=whole_sims / (ms * 1e-3) / steady_rate, mean_game_plies=sum(lengths) / max(1, len(lengths)),
+               min_game_plies=min(lengths) if lengths else 0, max_game_plies=max(lengths) if lengths else 0,
+               config=dict(workload=arm.workload(), total_games=total, slots=a.games, num_moves=bg.num_moves, resign=a.resign),
                pool=st, trees_dropped=bg.trees_dropped)
     if rank == 0:
         print(json.dumps(out))

@@ -77,7 +77,8 @@ class BatchedGames(object):
         n_games: concurrent games (slots in HBM); n_total: games to play in all (default n_games) — with more
         games than slots, a slot starts its next game as soon as one ends.
         resign: (resign_model1, resign_model2), each None, a float, or an array[G] (per slot; on_game_start(game_id)
-        may return a (r1, r2) pair for the game that is starting, e.g. from a calibration in progress).
+        may return a (r1, r2) pair for the game that is starting, e.g. from a calibration in progress, or a dict
+        {'resign': (r1, r2), 'num_moves': n} to cap that game's length, or False to skip the id).
         on_game_end(game_id, game_data) is called as each game finishes.
         rngs: optional list of per-slot rng objects (parity runs); else one shared `rng`; rng_for_game(game_id)
         hands each starting game its own rng (parity runs with more games than slots)."""
@@ -339,6 +340,7 @@ class BatchedGames(object):
         self.player = np.ones(G, np.int32)          # move_data['player'] (lags one ply, self_play.py:236)
         self.moves_rec = [[] for _ in range(G)]
         self.move_n = np.zeros(G, np.int32)         # ply counter of the game in each slot
+        self.num_moves_slot = np.full(G, self.num_moves, np.int32)     # ply cap of the game in each slot
         self.slot_game = np.full(G, -1, np.int64)   # id of the game a slot is playing
         self.next_game = 0
         self.results = {}
@@ -375,6 +377,10 @@ class BatchedGames(object):
             self.player[g] = 1
             self.moves_rec[g] = []
             self.move_n[g] = 0
+            self.num_moves_slot[g] = self.num_moves
+            if isinstance(r, dict):                 # per-game settings: {'resign': (r1, r2), 'num_moves': n}
+                self.num_moves_slot[g] = r.get('num_moves', self.num_moves)
+                r = r.get('resign')
             if r is not None:
                 r1, r2 = r
                 self.resign[0][g] = np.nan if r1 is None else r1
@@ -407,7 +413,7 @@ class BatchedGames(object):
         e, G, S, A = self.eng, self.G, self.S, self.A
         active, cur_model = self.active, self.cur_model
         # games that have played all their moves end here (the reference's `for move_n in range(num_moves)`)
-        over = active & (self.move_n >= self.num_moves)
+        over = active & (self.move_n >= self.num_moves_slot)
         if over.any():
             active &= ~over
             self._end_games(np.nonzero(over)[0])
