@@ -511,7 +511,7 @@ def run_full_games(a, arm, rank, world):
     steady_rate = (bg.sim_count - s0) / (e0.elapsed_time(e1) * 1e-3)
     out = dict(metric="selfplay_whole_games", value=whole_sims / (ms * 1e-3), unit="simulations/s", n_gpus=world,
                games=len(lengths), games_per_hour=len(lengths) / (ms * 1e-3) * 3600, plies_stepped=plies, ms_total=ms,
-               slot_occupancy=whole_sims / max(1, steady), steady_state_sims_per_s=steady_rate,
+               mean_active_fraction=whole_sims / max(1, steady), steady_state_sims_per_s=steady_rate,
                whole_run_over_steady_state=whole_sims / (ms * 1e-3) / steady_rate, mean_game_plies=sum(lengths) / max(1, len(lengths)),
                min_game_plies=min(lengths) if lengths else 0, max_game_plies=max(lengths) if lengths else 0,
                config=dict(workload=arm.workload(), total_games=total, slots=a.games, num_moves=bg.num_moves, resign=a.resign),

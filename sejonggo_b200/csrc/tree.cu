@@ -122,6 +122,7 @@ __device__ int free_subtree(const Pool &pool, int start, int keep, int lane)
     if (lane == 0) pb[start].parent_block = -1;                      // list terminator
     __syncwarp();
     int head = start, freed = 0;
+    int mine = -1;                                                   // lane (freed % 32) holds the id freed at that count: 32 ids per push
     while (head >= 0) {
         const int b = head;
         int next = pb[b].parent_block;
@@ -135,11 +136,25 @@ __device__ int free_subtree(const Pool &pool, int start, int keep, int lane)
             if (ch >= 0) pb[ch].parent_block = higher ? succ : next;  // chain this block's children in front of the list
             next = __shfl_sync(SGO_FULL, ch, __ffs(bal) - 1);
         }
-        if (lane == 0) pool_push(pool, b);
+        if (lane == (freed & 31)) mine = b;
         freed++;
+        if ((freed & 31) == 0) {                                      // one atomic per 32 blocks instead of one per block
+            int pos = 0;
+            if (lane == 0) pos = atomicAdd(&pool.ctl[0], 32);
+            pos = __shfl_sync(SGO_FULL, pos, 0);
+            pool.free_list[pos + lane] = mine;
+        }
         __syncwarp();
         head = next;
     }
+    const int rest = freed & 31;
+    if (rest) {
+        int pos = 0;
+        if (lane == 0) pos = atomicAdd(&pool.ctl[0], rest);
+        pos = __shfl_sync(SGO_FULL, pos, 0);
+        if (lane < rest) pool.free_list[pos + lane] = mine;
+    }
+    __syncwarp();
     return freed;
 }
 
