@@ -126,8 +126,12 @@ __device__ int free_subtree(const Pool &pool, int start, int keep, int lane)
     while (head >= 0) {
         const int b = head;
         int next = pb[b].parent_block;
+        int chs[SGO_AWORDS];
+#pragma unroll
+        for (int it = 0; it < SGO_AWORDS; it++) chs[it] = pb[b].child[it * 32 + lane];      // 12 independent loads in flight
+#pragma unroll
         for (int it = 0; it < SGO_AWORDS; it++) {
-            int ch = pb[b].child[it * 32 + lane];
+            int ch = chs[it];
             if (ch == keep) ch = -1;
             const unsigned bal = __ballot_sync(SGO_FULL, ch >= 0);
             if (!bal) continue;
