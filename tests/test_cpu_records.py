@@ -1,6 +1,7 @@
 """sgfsave-compatible record writer: layout, dtypes, Q14/Q15 semantics."""
 import os
 import numpy as np
+import pytest
 
 from oracle import oracle as o
 from sejonggo_b200 import sgfsave
