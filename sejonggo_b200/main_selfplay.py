@@ -43,7 +43,7 @@ class RankSelfPlay(object):
                  arena_blocks=None, gather_every=16, save=True):
         self.model, self.games, self.rank, self.world = model, list(games), rank, world
         self.size = size or conf['SIZE']
-        self.gather_every, self.save = gather_every, save
+        self.gather_every, self.save, self.mode = gather_every, save, mode
         self.cal = ResignationCalibrator()
         self.saved, self.rows_gathered = [], []
         self.bg = None
@@ -66,7 +66,7 @@ class RankSelfPlay(object):
         for r, t in enumerate(got):
             self.rows_gathered.append(int(t.numel()) * 4)
             self._pending[r] = np.concatenate([self._pending[r], t.cpu().numpy().view(np.uint32).reshape(-1, t.shape[1])])
-            done = games_from_rows(self._pending[r], self.size, names=(self.model.name, self.model.name), mode=self.bg.mode if self.bg else 'b')
+            done = games_from_rows(self._pending[r], self.size, names=(self.model.name, self.model.name), mode=self.mode)
             if done:
                 keep = ~np.isin(self._pending[r][:, 0], np.array(sorted(done), np.uint32))
                 self._pending[r] = self._pending[r][keep]
