@@ -73,7 +73,11 @@ def main():
     fn = lambda: e._ck(e.lib.sgo_tower_debug_conv(e.h, 0, n, 1, 0, 1, 2, e._stream()))
     padded = bool(os.environ.get("SGO_PADDED_LAYOUT"))
     # bit 8 (padded libraries): 289/324 of the tiles = an ideal pad-free kernel; bit 16 (dense libraries): all lane masks zero = what the masks cost
-    for name, data, dbg in (("full", act, 0), ("ideal_tiles" if padded else "no_masks", act, 8 if padded else 16), ("zero_act", zero, 0), ("full_again", act, 0)):
+    variants = [("full", act, 0), ("ideal_tiles" if padded else "no_masks", act, 8 if padded else 16), ("zero_act", zero, 0)]
+    if not padded:      # where does the power go?  (ablated runs compute garbage: timing / clocks only)
+        variants += [("no_B_loads", act, 4), ("no_A_loads", act, 2), ("no_epilogue_traffic", act, 1), ("no_skip_loads", act, 64)]
+    variants.append(("full_again", act, 0))
+    for name, data, dbg in variants:
         os.environ["SGO_CONV_DEBUG"] = str(dbg)
         load(data)
         ms, mhz, pw = sustained(fn, secs)
@@ -84,7 +88,10 @@ def main():
         out["bound"] = dict(ideal_speedup=f / out["ideal_tiles"]["ms"], zero_operand_speedup=f / out["zero_act"]["ms"],
                             note="ideal_speedup is the most ANY pad-free tiling could gain on this kernel at this power cap")
     else:
-        out["bound"] = dict(mask_cost=f / out["no_masks"]["ms"], zero_operand_speedup=f / out["zero_act"]["ms"])
+        out["bound"] = dict(mask_cost=f / out["no_masks"]["ms"], zero_operand_speedup=f / out["zero_act"]["ms"],
+                            no_B_loads_speedup=f / out["no_B_loads"]["ms"], no_A_loads_speedup=f / out["no_A_loads"]["ms"],
+                            no_epilogue_traffic_speedup=f / out["no_epilogue_traffic"]["ms"], no_skip_loads_speedup=f / out["no_skip_loads"]["ms"],
+                            note="sustained, power-capped: a speed-up here is (mostly) the energy that part of the kernel costs")
     print(json.dumps(out, indent=1))
 
 
