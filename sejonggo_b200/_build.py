@@ -26,18 +26,20 @@ def _stale():
 
 
 ABLATE_SO = os.path.join(LIBDIR, "libsejonggo_b200_ablate.so")
+WIDETILES_SO = os.path.join(LIBDIR, "libsejonggo_b200_widetiles.so")      # A/B: tower layers on conv_wide.cuh's 512-row super-tiles (--wide-tiles)
 
 
-def build(force=False, verbose=False, ablate=False):
+def build(force=False, verbose=False, ablate=False, wide_tiles=False):
     """ablate=True builds a SECOND library with -DSGO_CONV_ABLATE (the conv kernel's timing-ablation switches read
-    from SGO_CONV_DEBUG; tools/conv_variants.py loads it through SGO_LIBRARY).  The product library has none."""
-    out = ABLATE_SO if ablate else SO
-    if not force and not ablate and not _stale():
+    from SGO_CONV_DEBUG; tools/conv_variants.py loads it through SGO_LIBRARY); wide_tiles=True one whose tower layers run
+    on conv_wide.cuh (a measured alternative, profiles/r02_conv_wide_tiles_ab.json).  The product library has neither."""
+    out = ABLATE_SO if ablate else (WIDETILES_SO if wide_tiles else SO)
+    if not force and not ablate and not wide_tiles and not _stale():
         return SO
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.isfile(os.path.join(CSRC, s))]
-    cmd = [nvcc] + NVCC_FLAGS + (["-DSGO_CONV_ABLATE"] if ablate else []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs
+    cmd = [nvcc] + NVCC_FLAGS + (["-DSGO_CONV_ABLATE"] if ablate else []) + (["-DSGO_CONV_WIDE_TILES"] if wide_tiles else []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout)
@@ -47,4 +49,4 @@ def build(force=False, verbose=False, ablate=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, ablate="--ablate" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, ablate="--ablate" in sys.argv, wide_tiles="--wide-tiles" in sys.argv))

@@ -41,6 +41,8 @@ struct sgo_tower {
     float *val_conv_w, *val_conv_b, *val_fc1_w, *val_fc1_b, *val_fc2_w, *val_fc2_b;
     __nv_bfloat16 *act[3];                  // [max_pos*PX][C]
     uint32_t *lane_masks;                   // [PX][PR_MASK_WORDS] disable-output-lane masks per tile alignment (conv_pair.cuh)
+    uint32_t *lane_masks_wide;              // [PX][WD_MASK_WORDS] the same per 512-row super-tile alignment (conv_wide.cuh)
+    struct WideMaps *wmaps;                 // [0..2] tensor maps of k_conv3x3_wide per activation buffer
     struct PairMaps *pmaps;                 // [0..2] tensor maps of the CTA-pair kernel per activation buffer (conv_pair.cuh); [3] = stem im2col;
                                             // [4], [5] = dense heads: policy / value feature matrix + the transposed dense weights (fp32)
     __nv_bfloat16 *stem_col;                // [max_pos*PX][TW_STEM_K] im2col of the input planes (0/1, +-1)
@@ -118,6 +120,7 @@ __device__ __forceinline__ void stg256(void *p, const uint32_t v[8])
 }
 
 #include "conv_pair.cuh"
+#include "conv_wide.cuh"
 
 // ------------------------------------------------------------------ stem
 __device__ __forceinline__ void sym_src_t(int S, int sym, int y, int x, int &sy, int &sx)
@@ -224,6 +227,25 @@ __global__ void k_lane_masks(int W, uint32_t *masks)
     uint32_t m = 0;
     for (int b = 0; b < 32; b++) {
         const int pix = (al + 32 * w + b) % PX, y = pix / W, x = pix - y * W;
+        if (x + dx < 0 || x + dx >= W || y + dy < 0 || y + dy >= W) m |= 1u << b;
+    }
+    masks[i] = m;
+}
+
+// the same for the 512-row super-tiles of conv_wide.cuh: [alignment][row block j][tap slot][8 words]; words 0-3 are the
+// leader CTA's rows (super-tile rows 128j .. 128j+127), words 4-7 its peer's (256 + 128j ..)
+__global__ void k_lane_masks_wide(int W, uint32_t *masks)
+{
+    const int PX = W * W;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= PX * WD_MASK_WORDS) return;
+    const int al = i / WD_MASK_WORDS, r = i - al * WD_MASK_WORDS, j = r / 72, t = (r % 72) >> 3, w = r & 7;
+    const int tp = t == 0 ? 4 : (t <= 4 ? t - 1 : t);        // tap_of(t)
+    const int dy = tp / 3 - 1, dx = tp % 3 - 1;
+    const int row0 = (w < 4 ? 0 : 256) + 128 * j + 32 * (w & 3);
+    uint32_t m = 0;
+    for (int b = 0; b < 32; b++) {
+        const int pix = (al + row0 + b) % PX, y = pix / W, x = pix - y * W;
         if (x + dx < 0 || x + dx >= W || y + dy < 0 || y + dy >= W) m |= 1u << b;
     }
     masks[i] = m;
@@ -378,6 +400,23 @@ static int make_maps(sgo_engine *e, sgo_tower *t)
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (rr != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(weights) failed");
     }
+    t->wmaps = new WideMaps[3];
+    memset(t->wmaps, 0, sizeof(WideMaps) * 3);
+    for (int i = 0; i < 3; i++) {                          // k_conv3x3_wide: half-slab activation boxes, 64 x 64 weight boxes
+        cuuint64_t dims[2] = {(cuuint64_t)TW_C, Q};
+        cuuint64_t strides[1] = {(cuuint64_t)TW_C * 2};
+        cuuint32_t box[2] = {TW_KCH, (cuuint32_t)(128 + t->W + 1)};
+        CUresult rr = enc(&t->wmaps[i].act, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)t->act[i], dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rr != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(wide activation box) failed");
+        cuuint64_t wdims[2] = {(cuuint64_t)TW_C, (cuuint64_t)(t->n_layers ? t->n_layers : 1) * 9 * TW_C};
+        cuuint32_t boxw[2] = {TW_KCH, 64};
+        rr = enc(&t->wmaps[i].w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)t->conv_w, wdims, strides, boxw, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rr != CUDA_SUCCESS) return sgo_fail(e, "cuTensorMapEncodeTiled(wide weights) failed");
+    }
     for (int i = 4; i < 6; i++) {                          // dense heads: fp32, 32 elements = 128 bytes per K chunk
         cuuint64_t dims[2] = {(cuuint64_t)t->feat_ld, (cuuint64_t)t->max_pos};
         cuuint64_t strides[1] = {(cuuint64_t)t->feat_ld * 4};
@@ -403,7 +442,8 @@ static void tower_free(sgo_tower *t)
     cudaFree(t->val_conv_w); cudaFree(t->val_conv_b); cudaFree(t->val_fc1_w); cudaFree(t->val_fc1_b);
     cudaFree(t->val_fc2_w); cudaFree(t->val_fc2_b);
     for (int i = 0; i < 3; i++) cudaFree(t->act[i]);
-    cudaFree(t->err); cudaFree(t->lane_masks);
+    cudaFree(t->err); cudaFree(t->lane_masks); cudaFree(t->lane_masks_wide);
+    delete[] t->wmaps;
     cudaFree(t->stem_col); cudaFree(t->stem_wb); cudaFree(t->head_w4); cudaFree(t->head_b4);
     cudaFree(t->featp); cudaFree(t->featv); cudaFree(t->head_wt); cudaFree(t->head_bias); cudaFree(t->hbuf);
     delete[] t->pmaps;
@@ -467,6 +507,9 @@ extern "C" int sgo_tower_load_weights(sgo_engine *e, int32_t slot, const sgo_tow
     SGO_CUDA_OK(e, cudaMalloc(&t->lane_masks, sizeof(uint32_t) * (size_t)t->PX * PR_MASK_WORDS));
     k_lane_masks<<<(t->PX * PR_MASK_WORDS + 255) / 256, 256, 0, S_(stream)>>>(t->W, t->lane_masks);
     SGO_CUDA_OK(e, cudaGetLastError());
+    SGO_CUDA_OK(e, cudaMalloc(&t->lane_masks_wide, sizeof(uint32_t) * (size_t)t->PX * WD_MASK_WORDS));
+    k_lane_masks_wide<<<(t->PX * WD_MASK_WORDS + 255) / 256, 256, 0, S_(stream)>>>(t->W, t->lane_masks_wide);
+    SGO_CUDA_OK(e, cudaGetLastError());
     size_t col_bytes = (size_t)max_positions * t->PX * TW_STEM_K * sizeof(__nv_bfloat16);
     SGO_CUDA_OK(e, cudaMalloc(&t->stem_col, col_bytes));
     SGO_CUDA_OK(e, cudaMemsetAsync(t->stem_col, 0, col_bytes, S_(stream)));
@@ -501,6 +544,7 @@ extern "C" int sgo_tower_load_weights(sgo_engine *e, int32_t slot, const sgo_tow
     cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev);
     SGO_CUDA_OK(e, cudaFuncSetAttribute(k_conv3x3_pair<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM_BYTES));
     SGO_CUDA_OK(e, cudaFuncSetAttribute(k_conv3x3_pair<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM_BYTES));
+    SGO_CUDA_OK(e, cudaFuncSetAttribute(k_conv3x3_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, WD_SMEM_BYTES));
     int rc = make_maps(e, t);
     if (rc) return rc;
     SGO_CUDA_OK(e, cudaStreamSynchronize(S_(stream)));
@@ -538,6 +582,16 @@ static int launch_conv(sgo_engine *e, sgo_tower *t, int n, int layer, int in, in
     pa.featp = t->featp; pa.featv = t->featv; pa.feat_ld = t->feat_ld;
     pa.outf = nullptr; pa.ldo = pa.ncols = pa.n_valid = 0;
     int pairs = t->sm_count / 2;
+#ifdef SGO_CONV_WIDE_TILES
+    if (layer >= 0) {                           // A/B only (profiles/r02_conv_wide_tiles_ab.json): 512-row super-tiles, weight traffic halved (conv_wide.cuh)
+        pa.n_tiles = (pa.Q + 511) / 512;
+        pa.masks = t->lane_masks_wide;
+        if (pairs > pa.n_tiles) pairs = pa.n_tiles;
+        k_conv3x3_wide<<<2 * pairs, TW_THREADS, WD_SMEM_BYTES, S_(stream)>>>(t->wmaps[in], pa);
+        SGO_LAUNCHED(e);
+        return 0;
+    }
+#endif
     if (pairs > pa.n_tiles) pairs = pa.n_tiles;
     k_conv3x3_pair<0><<<2 * pairs, TW_THREADS, PR_SMEM_BYTES, S_(stream)>>>(t->pmaps[layer >= 0 ? in : 3], pa);
     SGO_LAUNCHED(e);
