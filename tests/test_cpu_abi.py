@@ -30,3 +30,12 @@ def test_no_cpu_fallback():
     cfg = _abi.SgoConfig(device=0, size=9, n_games=1, trees_per_game=1, max_leaves=1, arena_blocks=2, komi=5.5)
     h = C.c_void_p()
     assert _abi.load().sgo_create(C.byref(cfg), C.byref(h)) != 0
+
+
+def test_product_library_has_no_ablation_switch():
+    """The conv kernel's timing ablations (SGO_CONV_DEBUG) exist only in the --ablate build: the shipped library must not
+    read an environment variable that makes the timed kernel skip work."""
+    from sejonggo_b200 import _build
+    so = _build.build()
+    blob = open(so, "rb").read()
+    assert b"SGO_CONV_DEBUG" not in blob and b"getenv" not in blob
