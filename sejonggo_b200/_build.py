@@ -34,12 +34,15 @@ def build(force=False, verbose=False, ablate=False, wide_tiles=False):
     from SGO_CONV_DEBUG; tools/conv_variants.py loads it through SGO_LIBRARY); wide_tiles=True one whose tower layers run
     on conv_wide.cuh (a measured alternative, profiles/r02_conv_wide_tiles_ab.json).  The product library has neither."""
     out = ABLATE_SO if ablate else (WIDETILES_SO if wide_tiles else SO)
-    if not force and not ablate and not wide_tiles and not _stale():
+    extra = os.environ.get("SGO_NVCC_EXTRA", "").split()          # ad-hoc A/B variants: SGO_NVCC_EXTRA="-DPR_COALESCED_STORE=0" SGO_BUILD_OUT=<path>
+    if extra:
+        out = os.environ.get("SGO_BUILD_OUT") or os.path.join(LIBDIR, "libsejonggo_b200_variant.so")
+    if not force and not ablate and not wide_tiles and not extra and not _stale():
         return SO
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.isfile(os.path.join(CSRC, s))]
-    cmd = [nvcc] + NVCC_FLAGS + (["-DSGO_CONV_ABLATE"] if ablate else []) + (["-DSGO_CONV_WIDE_TILES"] if wide_tiles else []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs
+    cmd = [nvcc] + NVCC_FLAGS + (["-DSGO_CONV_ABLATE"] if ablate else []) + (["-DSGO_CONV_WIDE_TILES"] if wide_tiles else []) + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout)

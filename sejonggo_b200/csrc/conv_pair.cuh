@@ -39,6 +39,11 @@
 #else
 #define PR_DBG(bit) false                // the shipped library has no switch that makes the timed kernel skip work
 #endif
+#ifndef PR_COALESCED_STORE
+#define PR_COALESCED_STORE 1            // epilogue stores staged through shared memory so that a warp writes whole 128-B lines
+#endif
+#define PR_STAGE_PITCH 144              // bytes per staged row: 128 + 16, so that 8 lanes writing / reading 16 B each hit 32 distinct banks
+#define PR_STAGE_BYTES (4 * 32 * PR_STAGE_PITCH)   // one 32-row x 128-B staging tile per epilogue warp
 #define PR_SLABS 3
 #define PR_SLAB_BYTES (21 * 1024)                  // >= (128 + 2 * (W + 1)) * 128 for W <= 19
 #define PR_MASK_WORDS 72                           // 9 taps (issue order) x 8 words of disable-output-lane mask per tile alignment
@@ -81,7 +86,8 @@ struct PairSmemTail {
     float bias[TW_C];
     float4 w4[TW_C];
 };
-#define PR_SMEM_BYTES (PR_SLABS * PR_SLAB_BYTES + PR_BSTAGES * PR_B_BYTES + (int)sizeof(PairSmemTail) + 1024)
+#define PR_TAIL_BYTES (((int)sizeof(PairSmemTail) + 15) / 16 * 16)
+#define PR_SMEM_BYTES (PR_SLABS * PR_SLAB_BYTES + PR_BSTAGES * PR_B_BYTES + PR_TAIL_BYTES + PR_STAGE_BYTES + 1024)
 
 #define PR_PEER_MASK 0xFEFFFFFFu      // cute::Sm100MmaPeerBitMask: clear the CTA-rank bit -> leader CTA's smem
 
@@ -175,6 +181,7 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *smem_b = smem + PR_SLABS * PR_SLAB_BYTES;
     PairSmemTail *tail = reinterpret_cast<PairSmemTail *>(smem_b + PR_BSTAGES * PR_B_BYTES);
+    uint8_t *stage_base = reinterpret_cast<uint8_t *>(tail) + PR_TAIL_BYTES;      // epilogue store staging (PR_STAGE_BYTES)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
@@ -386,8 +393,8 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
                 }
                 uint32_t v[32];
                 tmem_ld32(t_addr + c * 32, v);
+                uint32_t ow[16];
                 if (valid) {
-                    uint32_t ow[16];
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
                         float f0 = __uint_as_float(v[2 * j]) + tail->bias[c * 32 + 2 * j];
@@ -406,17 +413,37 @@ k_conv3x3_pair(const __grid_constant__ PairMaps maps, PairArgs a)
                             h0 = fmaf(f1, wb.x, h0); h1 = fmaf(f1, wb.y, h1); h2 = fmaf(f1, wb.z, h2); h3 = fmaf(f1, wb.w, h3);
                         }
                     }
+#if !PR_COALESCED_STORE
                     if (a.out && !PR_DBG(32)) {
-#if PR_WIDE_LDST
                         stg256(a.out + gofs + c * 32, ow);
                         stg256(a.out + gofs + c * 32 + 16, ow + 8);
-#else
-                        uint4 *op = reinterpret_cast<uint4 *>(a.out + gofs + c * 32);
-#pragma unroll
-                        for (int j = 0; j < 4; j++) op[j] = reinterpret_cast<const uint4 *>(ow)[j];
+                    }
 #endif
+                }
+#if PR_COALESCED_STORE
+                // A lane holds 64 B of ITS row: stored directly, a warp instruction touches 32 different 128-B lines with one
+                // 32-B sector each.  Staged through shared memory (two iterations = 128 B per row), eight lanes then write
+                // one whole line: a quarter of the L1 / L2 transactions for the same bytes.
+                if (a.out && !PR_DBG(32)) {                          // (warp-uniform)
+                    uint8_t *st = stage_base + (size_t)qw * (32 * PR_STAGE_PITCH);
+                    uint4 *mine = reinterpret_cast<uint4 *>(st + lane * PR_STAGE_PITCH + (c & 1) * 64);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) mine[j] = reinterpret_cast<const uint4 *>(ow)[j];
+                    if (c & 1) {
+                        __syncwarp();
+                        const int q_warp = tile * 256 + (int)rank * 128 + qw * 32;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            const int row = 4 * k + (lane >> 3);
+                            const uint4 val = *reinterpret_cast<const uint4 *>(st + row * PR_STAGE_PITCH + (lane & 7) * 16);
+                            const int qq = q_warp + row;
+                            if (qq < a.Q && !PR_DBG(1))
+                                *reinterpret_cast<uint4 *>(a.out + (size_t)qq * TW_C + (c - 1) * 32 + (lane & 7) * 8) = val;
+                        }
+                        __syncwarp();
                     }
                 }
+#endif
             }
             tc_fence_before();
             mbar_arrive_leader(&tail->tmem_empty[acc]);
