@@ -40,10 +40,10 @@
 #define PR_DBG(bit) false                // the shipped library has no switch that makes the timed kernel skip work
 #endif
 #ifndef PR_COALESCED_STORE
-#define PR_COALESCED_STORE 1            // epilogue stores staged through shared memory so that a warp writes whole 128-B lines
-#endif
+#define PR_COALESCED_STORE 0            // 1: epilogue stores staged through shared memory so that a warp writes whole 128-B lines.  Measured:
+#endif                                  // convs +0.6%, stem -13%, forward +0.4% (profiles/r02_conv_coalesced_store_ab.json) — not adopted
 #define PR_STAGE_PITCH 144              // bytes per staged row: 128 + 16, so that 8 lanes writing / reading 16 B each hit 32 distinct banks
-#define PR_STAGE_BYTES (4 * 32 * PR_STAGE_PITCH)   // one 32-row x 128-B staging tile per epilogue warp
+#define PR_STAGE_BYTES (PR_COALESCED_STORE ? 4 * 32 * PR_STAGE_PITCH : 0)   // one 32-row x 128-B staging tile per epilogue warp
 #define PR_SLABS 3
 #define PR_SLAB_BYTES (21 * 1024)                  // >= (128 + 2 * (W + 1)) * 128 for W <= 19
 #define PR_MASK_WORDS 72                           // 9 taps (issue order) x 8 words of disable-output-lane mask per tile alignment
