@@ -201,6 +201,12 @@ def test_run_evaluation_bookkeeping(tmp_path):
             assert ew.run_evaluation(best, latest, concurrent=4, mode=mode, num_moves=12) == (0, 0)
             if mode == 'b':                                                                # eval games double as training data
                 assert os.path.isdir(os.path.join(conf['GAMES_DIR'], latest_name, "eval_game_000", "move_000"))
+                assert len(latest.calls) > 0            # the candidate network really was evaluated (LATEST_SYM -> latest model)
+        # ... unless the reference's Q21 is asked for: LATEST_SYM is then served by the BEST network and `latest` is never called
+        conf.update(EVAL_DIR=str(tmp_path / "eval_q21"))
+        best, latest = FakeModel("model_1", salt=1, sharp=True), FakeModel("model_4", salt=2, sharp=True)
+        wins, total = ew.run_evaluation(best, latest, concurrent=3, n_games=3, mode='b', num_moves=6, reference_q21=True)
+        assert total == 3 and len(latest.calls) == 0 and len(best.calls) > 0
         assert ew.run_evaluation(best, best, mode='a') == (0, 0)                           # "No new trained model"
     finally:
         conf.clear()
