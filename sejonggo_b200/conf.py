@@ -25,6 +25,7 @@ conf = {
     'MODEL_DIR': 'sp_models',
     'EVAL_DIR': 'sp_eval_games',
     'GAMES_DIR': 'sp_eval_games',
+    'SGF_ENABLED': False,
     'BEST_MODEL': 'best_model.npz',      # the reference's best_model.h5 (Keras .h5 I/O is out of scope)
     # engine-only knobs
     'CONCURRENT_GAMES': 1024,

@@ -73,12 +73,62 @@ def _save(root, model_name, game_no, game_data, fmt, size):
 
 def save_self_play_data(model_name, game_no, game_data, size=None):
     """sgfsave.py:49-79."""
-    return _save(conf['SELF_PLAY_DIR'], model_name, game_no, game_data, "game_%05d", size)
+    out = _save(conf['SELF_PLAY_DIR'], model_name, game_no, game_data, "game_%05d", size)
+    if conf.get('SGF_ENABLED'):
+        save_game_sgf(model_name, game_no, game_data, size=size)
+    return out
 
 
 def save_game_data(model_name, game_n, game_data, game_name="game", size=None):
     """sgfsave.py:40-46 (evaluation games, GAMES_DIR)."""
-    return _save(conf.get('GAMES_DIR', 'sp_eval_games'), model_name, game_n, game_data, game_name + "_%03d", size)
+    out = _save(conf.get('GAMES_DIR', 'sp_eval_games'), model_name, game_n, game_data, game_name + "_%03d", size)
+    if conf.get('SGF_ENABLED'):
+        save_game_sgf(model_name, game_n, game_data, size=size)
+    return out
+
+
+def _sgf_escape(text):
+    return str(text).replace("\\", "\\\\").replace("]", "\\]")
+
+
+def real_board(board, size):
+    """play.get_real_board (play.py:106-112): +1 black / -1 white / 0 empty from planes 0, 1 and the side to move."""
+    b = np.asarray(board)
+    if b.ndim == 1:
+        b = unpack_board(b, size)
+    own, opp, tm = b[0, :, :, 0], b[0, :, :, 1], int(b[0, 0, 0, 16])
+    return ((own - opp) * tm).astype(np.int32)
+
+
+def save_game_sgf(model_name, game_n, game_data, size=None):
+    """sgfsave.py:130-167 without sgfmill: GAMES_DIR/<model>/game_%03d.sgf (the number is bumped while the file exists), an
+    FF[4] game record with PB / PW / KM / RE and one node per ply: colour from move_data['player'] (which lags one ply in
+    the reference, self_play.py:236 — reproduced), the move in SGF letters (column x, row y from the top; pass = empty),
+    and the comment "Value <v>\n <board after the move>" taken, like the reference, from the NEXT ply's board (the last
+    ply wraps around to the first)."""
+    S = size or conf['SIZE']
+    head = "(;FF[4]CA[UTF-8]GM[1]SZ[%d]PB[%s]PW[%s]KM[%s]RE[%s]" % (
+        S, _sgf_escape(game_data['modelB_name']), _sgf_escape(game_data['modelW_name']), conf['KOMI'], _sgf_escape(game_data['result']))
+    nodes = []
+    moves = game_data['moves']
+    for md in moves:
+        color = 'B' if md['player'] == 1 else 'W'
+        x, y = md['move']
+        coord = "" if y == S else chr(97 + x) + chr(97 + y)
+        nxt = moves[(md['move_n'] + 1) % len(moves)]['board']
+        comment = "Value %s" % md['value']
+        if nxt is not None:
+            comment += "\n %s" % real_board(nxt, S)
+        nodes.append(";%s[%s]C[%s]" % (color, coord, _sgf_escape(comment)))
+    directory = os.path.join(conf.get('GAMES_DIR', 'sp_eval_games'), model_name)
+    os.makedirs(directory, exist_ok=True)
+    filename = os.path.join(directory, "game_%03d.sgf" % game_n)
+    while os.path.isfile(filename):
+        game_n += 1
+        filename = os.path.join(directory, "game_%03d.sgf" % game_n)
+    with open(filename, "w") as f:
+        f.write(head + "".join(nodes) + ")\n")
+    return filename
 
 
 def npz_to_h5(root):

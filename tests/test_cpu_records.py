@@ -112,3 +112,35 @@ def test_record_rows_round_trip_and_partial_games():
             assert np.array_equal(a['policy'], np.asarray(b['policy'], np.float32))
     with pytest.raises(ValueError):
         records.games_from_rows(allrows[1:], S)          # a ply row of a finished game is missing
+
+
+def test_sgf_game_record(tmp_path):
+    """sgfsave.save_game_sgf (sgfsave.py:130-167, written without sgfmill): properties, one node per ply, colours from the
+    reference's lagging `player` field, SGF letter coordinates (column x, row y from the top, empty = pass), file
+    number bumped on a clash; switched on by conf['SGF_ENABLED'] from save_self_play_data like the reference."""
+    import re
+    from oracle import game_loop as gl
+    from oracle.fake_eval import FakeModel
+    old = dict(conf)
+    try:
+        conf.update(SIZE=5, KOMI=5.5, GAMES_DIR=str(tmp_path / "games"), SELF_PLAY_DIR=str(tmp_path / "sp"), SGF_ENABLED=True)
+        m = FakeModel("model_8", salt=4, sharp=True)
+        gd = gl.play_game(m, m, 8, 2, self_play=True, num_moves=30, size=5, mcts_batch_size=4, rng=gl.SeededRng(6))
+        sgfsave.save_self_play_data("model_8", 0, gd, size=5)
+        sgfsave.save_self_play_data("model_8", 0, gd, size=5)            # the same game number again: sample dirs and sgf both bump
+        files = sorted(os.listdir(tmp_path / "games" / "model_8"))
+        assert files == ["game_000.sgf", "game_001.sgf"]
+        text = open(tmp_path / "games" / "model_8" / "game_000.sgf").read()
+        assert text.startswith("(;FF[4]") and text.rstrip().endswith(")")
+        props = dict(re.findall(r"(SZ|PB|PW|KM|RE)\[([^\]]*)\]", text))
+        assert props == {"SZ": "5", "PB": "model_8", "PW": "model_8", "KM": "5.5", "RE": gd['result']}
+        nodes = re.findall(r";([BW])\[([a-z]{0,2})\]C\[", text)
+        assert len(nodes) == len(gd['moves'])
+        for (color, coord), md in zip(nodes, gd['moves']):
+            x, y = md['move']
+            assert color == ('B' if md['player'] == 1 else 'W')
+            assert coord == ("" if y == 5 else "abcde"[x] + "abcde"[y])
+        assert "Value " in text
+    finally:
+        conf.clear()
+        conf.update(old)
