@@ -36,7 +36,7 @@ class SejongGoEngine(object):
         self.move = 1
         steps = int(mcts_simulations / self.batch)
         self.eng = Engine(size=self.S, n_games=1, trees_per_game=1, max_leaves=self.batch,
-                          arena_blocks=max(256, 4 * (steps * self.batch + self.batch)), komi=conf['KOMI'], device=device)
+                          arena_blocks=max(1024, 64 * (steps * self.batch + self.batch)), komi=conf['KOMI'], device=device)   # one game: the whole pool is its tree's (680 MB at 1,600 sims)
         self.eng.reset()
         self.eng.tree_reset()
         if board is not None:
