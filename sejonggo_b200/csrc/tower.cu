@@ -213,6 +213,8 @@ k_stem_im2col(const Board *boards, const int32_t *index, const int32_t *syms, in
     }
 }
 
+#include "stem_fused.cuh"
+
 // disable-output-lane masks of the 3x3 "same" convolution over the dense q layout (conv_pair.cuh): for a pair tile whose first
 // row is pixel `al` of a position, bit i of word w of tap-slot t is set when row 32w + i must NOT receive tap tap_of(t),
 // i.e. when its (dy, dx) neighbour lies off the W x W board.  One thread per (alignment, tap slot, word).
@@ -545,6 +547,7 @@ extern "C" int sgo_tower_load_weights(sgo_engine *e, int32_t slot, const sgo_tow
     SGO_CUDA_OK(e, cudaFuncSetAttribute(k_conv3x3_pair<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM_BYTES));
     SGO_CUDA_OK(e, cudaFuncSetAttribute(k_conv3x3_pair<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM_BYTES));
     SGO_CUDA_OK(e, cudaFuncSetAttribute(k_conv3x3_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, WD_SMEM_BYTES));
+    SGO_CUDA_OK(e, cudaFuncSetAttribute(k_stem_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM_BYTES));
     int rc = make_maps(e, t);
     if (rc) return rc;
     SGO_CUDA_OK(e, cudaStreamSynchronize(S_(stream)));
@@ -643,12 +646,23 @@ extern "C" int sgo_tower_forward(sgo_engine *e, int32_t slot, int32_t which, con
     const bool prof = t->prof_on && t->prof_n < TW_PROF_MAX;
     cudaEvent_t *pe = prof ? t->prof_ev + (size_t)t->prof_n * 4 : nullptr;
     if (prof) cudaEventRecord(pe[0], S_(stream));
-    // stem = im2col from the bitboards + one pair-kernel GEMM (K = 192) with the bias/ReLU epilogue
-    int g2 = (n + IM_NP - 1) / IM_NP;
-    if (g2 > 8 * t->sm_count) g2 = 8 * t->sm_count;
-    k_stem_im2col<<<g2, IM_THREADS, 0, S_(stream)>>>(boards, d_index, d_sym, n, t->S, t->stem_col);
-    SGO_LAUNCHED(e);
-    {
+    // stem = one GEMM (K = 192) over the im2col of the bitboards, bias/ReLU epilogue
+#ifndef SGO_STEM_SEPARATE                           // -DSGO_STEM_SEPARATE: the A/B baseline of profiles/r02_stem_fused_ab.json
+    if (t->n_blocks > 0) {                          // im2col built inside the GEMM's producer (stem_fused.cuh)
+        StemArgs sa;
+        sa.boards = boards; sa.index = d_index; sa.syms = d_sym; sa.n = n; sa.S = t->S; sa.W = t->W; sa.PX = t->PX;
+        sa.Q = n * t->PX; sa.n_tiles = (sa.Q + 255) / 256; sa.bias = t->stem_b; sa.out = t->act[0]; sa.err = t->err;
+        int pairs = t->sm_count / 2;
+        if (pairs > sa.n_tiles) pairs = sa.n_tiles;
+        k_stem_fused<<<2 * pairs, SF_THREADS, SF_SMEM_BYTES, S_(stream)>>>(t->pmaps[3], sa);
+        SGO_LAUNCHED(e);
+    } else
+#endif
+    {                                               // towers without blocks: the stem GEMM's epilogue carries the 1x1 head convs
+        int g2 = (n + IM_NP - 1) / IM_NP;
+        if (g2 > 8 * t->sm_count) g2 = 8 * t->sm_count;
+        k_stem_im2col<<<g2, IM_THREADS, 0, S_(stream)>>>(boards, d_index, d_sym, n, t->S, t->stem_col);
+        SGO_LAUNCHED(e);
         int rc0 = launch_conv(e, t, n, -1, 3, 0, -1, stream, t->n_blocks == 0);
         if (rc0) return rc0;
     }
