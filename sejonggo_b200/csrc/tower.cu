@@ -1,9 +1,10 @@
 // tower.cu — the residual policy/value tower of model.py:55-96 on sm_100a.
 //
-//   stem   Conv3x3 "valid" 17->C on the SxS input planes + BN + ReLU (model.py:57-61) as
-//          im2col straight from the packed bitboards (input-plane construction play.py:295-299
-//          and the symmetry gather symmetry.py:45-114 fused in; values 0/1/+-1 are exact in
-//          bf16) followed by ONE tensor-core GEMM (K = 153 -> 192) through the pair kernel.
+//   stem   Conv3x3 "valid" 17->C on the SxS input planes + BN + ReLU (model.py:57-61) as ONE
+//          tensor-core GEMM (K = 153 -> 192) whose A tiles are the im2col of the packed bitboards,
+//          built in shared memory by the kernel's producer warps (stem_fused.cuh; input-plane
+//          construction play.py:295-299 and the symmetry gather symmetry.py:45-114 fused in; values
+//          0/1/+-1 are exact in bf16).  Block-less towers (tests) use k_stem_im2col + the pair kernel.
 //   tower  2*N_RESIDUAL_BLOCKS Conv3x3 "same" C->C (+BN folded, +skip, ReLU): implicit GEMMs on
 //          CTA pairs — TMA boxes per filter tap, tcgen05.mma.cta_group::2, double-buffered TMEM
 //          accumulators (conv_pair.cuh).
@@ -138,7 +139,8 @@ __device__ __forceinline__ void sym_src_t(int S, int sym, int y, int x, int &sy,
     }
 }
 
-// Stem as a tensor-core GEMM: im2col of the (symmetry-transformed) input planes straight from
+// The stem's im2col as a tensor in HBM (block-less towers and the -DSGO_STEM_SEPARATE baseline; the product path builds
+// the same rows in shared memory, stem_fused.cuh): the (symmetry-transformed) input planes straight from
 // the packed bitboards: col[row(y), x][tap*17 + p] = plane p at (y+ky, x+kx)  (valid conv, Q11).
 // Every value is 0, 1 or +-1, exact in bf16.  A block takes IM_NP positions at a time: first the
 // 16 stone planes of every cell as one 16-bit mask in shared memory, then one thread per output
