@@ -34,7 +34,7 @@ def build(force=False, verbose=False, ablate=False, wide_tiles=False):
     from SGO_CONV_DEBUG; tools/conv_variants.py loads it through SGO_LIBRARY); wide_tiles=True one whose tower layers run
     on conv_wide.cuh (a measured alternative, profiles/r02_conv_wide_tiles_ab.json).  The product library has neither."""
     out = ABLATE_SO if ablate else (WIDETILES_SO if wide_tiles else SO)
-    extra = os.environ.get("SGO_NVCC_EXTRA", "").split()          # ad-hoc A/B variants: SGO_NVCC_EXTRA="-DPR_COALESCED_STORE=0" SGO_BUILD_OUT=<path>
+    extra = os.environ.get("SGO_NVCC_EXTRA", "").split()          # ad-hoc A/B variants: SGO_NVCC_EXTRA="-DPR_COALESCED_STORE=1" (or -DSGO_STEM_SEPARATE) SGO_BUILD_OUT=<path>
     if extra:
         out = os.environ.get("SGO_BUILD_OUT") or os.path.join(LIBDIR, "libsejonggo_b200_variant.so")
     if not force and not ablate and not wide_tiles and not extra and not _stale():
