@@ -3,7 +3,6 @@ is a dead wrapper — SURVEY §0).  Same names, argument meaning and error behav
 on the reference's own board tensor int32 [n,S,S,17]; the work happens in the CUDA
 rules kernels (csrc/rules.cu) through the C ABI.  Batched variants take n boards."""
 import numpy as np
-import torch
 
 from .conf import conf
 from .engine import Engine, EngineError

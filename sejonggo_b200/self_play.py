@@ -3,10 +3,9 @@ Same function names, positional order, defaults and game_data keys
 (self_play.py:164, 293, 343); `play_games` is the batched form they wrap."""
 import os
 from random import random
-import numpy as np
 
 from .conf import conf
-from .batched import BatchedGames, HostRng
+from .batched import BatchedGames
 from .sgfsave import save_game_data, save_self_play_data
 
 

@@ -10,7 +10,6 @@ games (:115-118) and the per-game save through sgfsave.save_self_play_data.  scp
 import os
 from random import random
 
-import numpy as np
 
 from .conf import conf
 from . import predicting_queue_worker as pq

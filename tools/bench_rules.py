@@ -1,7 +1,6 @@
 """Micro-benchmark of the board kernels (HBM-bound rows of SURVEY §8d): CUDA-event timed."""
 import json
 import sys
-import numpy as np
 import torch
 
 sys.path.insert(0, ".")

@@ -5,7 +5,6 @@ summaries of the stem / heads / board / tree kernels.
     python tools/fill_profiles_r02.py <tag> [round]"""
 import collections
 import csv
-import io
 import json
 import shutil
 import subprocess
