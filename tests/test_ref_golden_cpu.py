@@ -199,3 +199,45 @@ def test_back_prop():                             # tree_util_tests.py:139-193
     o.back_propagation((dict(count=0, p=0.5, value=1, mean_value=0, virtual_loss=0, subtree={}), [0]), t)
     assert t.count == 1 and t.value == 1 and t.mean_value == 1
     assert t.child(0).value == 1 and t.child(0).virtual_loss == 0
+
+
+class _Dummy(object):
+    """tests.py:34-49 DummyModel as a model object (mode A asks model.predict_on_batch)."""
+    name = "dummy"
+
+    def predict_on_batch(self, b):
+        return _dummy_eval(np.asarray(b))
+
+
+class _IdentityRng(object):
+    """The PlayTestCase setup (tests.py / async_sim_tests.py:1046-1052): SYMMETRIES cut to the identity, a seeded RNG."""
+
+    def __init__(self, seed):
+        from oracle import game_loop as gl
+        self.inner = gl.SeededRng(seed)
+
+    def __getattr__(self, k):
+        return getattr(self.inner, k)
+
+    def symmetry(self):
+        return 0
+
+
+@pytest.mark.parametrize("self_play,sims,stop,num_moves,expect", [
+    (True, 8, 30, 5, 1),       # async_sim_tests.py:1059-1071 test_new_tree_called_once_self_play: one shared tree, re-rooted every ply
+    (False, 32, 0, 2, 2),      # async_sim_tests.py:1074-1089 test_new_tree_called_twice_evaluation: one tree per model
+])
+def test_new_tree_call_count(monkeypatch, self_play, sims, stop, num_moves, expect):
+    from oracle import game_loop as gl
+    calls = []
+    real = o.new_tree
+
+    def counting(*a, **k):
+        calls.append(1)
+        return real(*a, **k)
+
+    monkeypatch.setattr(o, "new_tree", counting)
+    m = _Dummy()
+    gd = gl.play_game(m, m, sims, stop, self_play=self_play, num_moves=num_moves, size=9, mcts_batch_size=8, rng=_IdentityRng(0))
+    assert len(gd['moves']) == num_moves
+    assert len(calls) == expect
